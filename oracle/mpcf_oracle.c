@@ -1,0 +1,204 @@
+/*
+ * oracle/mpcf_oracle.c — TEST INFRASTRUCTURE ONLY (see mpcf_oracle.h).
+ *
+ * Batch drivers around core.inc.h.  Build: `make -C oracle` (gcc -O2 -ffp-contract=off for the
+ * reproducible checker `libmpcf_oracle.so`; -O3 -march=native for the timing build
+ * `libmpcf_oracle_fast.so` used by bench.py's cpu_baseline leg).
+ */
+#include "mpcf_oracle.h"
+
+#include <complex.h>
+#include <math.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* real instantiation */
+#define SC double
+#define SUF(x) x##_r
+#define SIN sin
+#define COS cos
+#define EXP exp
+#include "core.inc.h"
+#undef SC
+#undef SUF
+#undef SIN
+#undef COS
+#undef EXP
+
+/* complex instantiation (complex-step derivatives) */
+#define SC double complex
+#define SUF(x) x##_c
+#define SIN csin
+#define COS ccos
+#define EXP cexp
+#include "core.inc.h"
+#undef SC
+#undef SUF
+#undef SIN
+#undef COS
+#undef EXP
+
+static int g_threads = 0;
+
+int mpcfo_set_threads(int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) { g_threads = nthreads; omp_set_num_threads(nthreads); }
+    return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+    (void)nthreads;
+    return 1;
+#endif
+}
+
+#define CHECK_N(m) do { if ((m)->n <= 0 || (m)->n > MPCFO_MAXN) return -1; } while (0)
+
+int mpcfo_rnea_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
+                     double *tau)
+{
+    CHECK_N(m);
+    int n = m->n;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], t[MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
+        rnea_r(m, a, b, c, t);
+        for (int i = 0; i < n; ++i) tau[i * U + u] = t[i];
+    }
+    return 0;
+}
+
+int mpcfo_fk_batch(const mpcfo_model *m, int frame, long U, const double *q, double *pos, double *rot)
+{
+    CHECK_N(m);
+    if (frame < 0 || frame >= m->nframes) return -2;
+    int n = m->n;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double a[MPCFO_MAXN], p[3], R[9];
+        for (int i = 0; i < n; ++i) a[i] = q[i * U + u];
+        frame_fk_r(m, frame, a, p, R);
+        for (int k = 0; k < 3; ++k) pos[k * U + u] = p[k];
+        for (int k = 0; k < 9; ++k) rot[k * U + u] = R[k];
+    }
+    return 0;
+}
+
+int mpcfo_jac_batch(const mpcfo_model *m, int frame, long U, const double *q, double *J)
+{
+    CHECK_N(m);
+    if (frame < 0 || frame >= m->nframes) return -2;
+    int n = m->n;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double a[MPCFO_MAXN], Jl[6 * MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) a[i] = q[i * U + u];
+        frame_jacobian_r(m, frame, a, Jl);
+        for (int k = 0; k < 6 * n; ++k) J[k * U + u] = Jl[k];
+    }
+    return 0;
+}
+
+int mpcfo_crba(const mpcfo_model *m, const double *q, double *M)
+{
+    CHECK_N(m);
+    crba_r(m, q, M);
+    return 0;
+}
+
+int mpcfo_aba_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *tau,
+                    double *qdd)
+{
+    CHECK_N(m);
+    int n = m->n, rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], t[MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = tau[i * U + u]; }
+        rc |= aba_r(m, a, b, c, t) != 0;
+        for (int i = 0; i < n; ++i) qdd[i * U + u] = t[i];
+    }
+    return rc ? -3 : 0;
+}
+
+int mpcfo_node_eval_ref_batch(const mpcfo_model *m, int nee, const int *ee_frames, double wsign, long U,
+                              const double *q, const double *qd, const double *qdd, const double *W,
+                              const double *T, double h, double *tau, double *qnext, double *Tnext)
+{
+    CHECK_N(m);
+    if (nee < 0 || nee > 8) return -2;
+    for (int e = 0; e < nee; ++e)
+        if (ee_frames[e] < 0 || ee_frames[e] >= m->nframes) return -2;
+    int n = m->n;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], Tl[MPCFO_MAXN], Wl[48];
+        double t[MPCFO_MAXN], qn[MPCFO_MAXN], Tn[MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) {
+            a[i] = q[i * U + u]; b[i] = qd[i * U + u];
+            c[i] = qdd ? qdd[i * U + u] : 0.0;
+            Tl[i] = T ? T[i * U + u] : 0.0;
+        }
+        for (int k = 0; k < 6 * nee; ++k) Wl[k] = W[k * U + u];
+        node_eval_ref_r(m, nee, ee_frames, wsign, a, b, c, Wl, Tl, h, t, qn, Tn);
+        for (int i = 0; i < n; ++i) {
+            tau[i * U + u] = t[i];
+            if (qnext) qnext[i * U + u] = qn[i];
+            if (Tnext) Tnext[i * U + u] = Tn[i];
+        }
+    }
+    return 0;
+}
+
+int mpcfo_step_rk4_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *tau,
+                         const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn)
+{
+    CHECK_N(m);
+    int n = m->n, rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double x[3 * MPCFO_MAXN], t[MPCFO_MAXN], xn[3 * MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) {
+            x[i] = q[i * U + u]; x[n + i] = qd[i * U + u]; x[2 * n + i] = f[i * U + u]; t[i] = tau[i * U + u];
+        }
+        rc |= step_rk4_r(m, x, t, dt_u ? dt_u[u] : dt, xn) != 0;
+        for (int i = 0; i < n; ++i) {
+            qn[i * U + u] = xn[i]; qdn[i * U + u] = xn[n + i]; fn[i * U + u] = xn[2 * n + i];
+        }
+    }
+    return rc ? -3 : 0;
+}
+
+int mpcfo_step_rk4_jvp_batch(const mpcfo_model *m, long U, const double *q, const double *qd,
+                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                             double *qdn, double *fn, double *jac)
+{
+    CHECK_N(m);
+    const int n = m->n, P = 4 * n + 1;
+    const double hstep = 1e-40;
+    int rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double complex x[3 * MPCFO_MAXN], t[MPCFO_MAXN], xn[3 * MPCFO_MAXN], h;
+        for (int d = 0; d < P; ++d) {
+            for (int i = 0; i < n; ++i) {
+                x[i] = q[i * U + u]; x[n + i] = qd[i * U + u]; x[2 * n + i] = f[i * U + u]; t[i] = tau[i * U + u];
+            }
+            h = dt_u ? dt_u[u] : dt;
+            /* seed direction d of (q, qd, tau, f, dt) */
+            if (d < 2 * n) x[d] += hstep * I;
+            else if (d < 3 * n) t[d - 2 * n] += hstep * I;
+            else if (d < 4 * n) x[d - n] += hstep * I; /* f lives at x[2n..3n) */
+            else h += hstep * I;
+            rc |= step_rk4_c(m, x, t, h, xn) != 0;
+            for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + d) * U + u] = cimag(xn[r]) / hstep;
+            if (d == 0 && qn)
+                for (int i = 0; i < n; ++i) {
+                    qn[i * U + u] = creal(xn[i]); qdn[i * U + u] = creal(xn[n + i]); fn[i * U + u] = creal(xn[2 * n + i]);
+                }
+        }
+    }
+    return rc ? -3 : 0;
+}

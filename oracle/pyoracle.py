@@ -1,0 +1,146 @@
+"""oracle/pyoracle.py — TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of the C oracle (oracle/mpcf_oracle.c).  Arrays are numpy float64 in the SoA
+layout of the C-ABI: `[component, U]`, C-contiguous.  Importers: tests/, __graft_entry__.smoke(),
+bench.py's cpu_baseline / `--impl reference` legs.  Nothing under mpc_fatigue_b200/ imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .urdf_model import Model
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+
+class _CModel(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("nframes", C.c_int), ("parent", _IP), ("jtype", _IP), ("Rp", _DP), ("pp", _DP),
+        ("mass", _DP), ("mc", _DP), ("Io", _DP), ("arm", _DP), ("fat", _DP), ("grav", C.c_double * 3),
+        ("fparent", _IP), ("fR", _DP), ("fp", _DP),
+    ]
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle libraries (checker + timing build) with the committed Makefile."""
+    args = ["make", "-C", _HERE, "-s"] + (["-B"] if force else [])
+    subprocess.run(args, check=True)
+
+
+def _load(fast: bool):
+    name = "libmpcf_oracle_fast.so" if fast else "libmpcf_oracle.so"
+    path = os.path.join(_HERE, "_build", name)
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    lib.mpcfo_set_threads.restype = C.c_int
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_DP)
+
+
+def _chk(a, rows, U):
+    assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (rows, U), (a.shape, (rows, U))
+    return a
+
+
+class Oracle:
+    """CPU oracle bound to one model.  `fast=True` selects the -O3 -march=native timing build."""
+
+    def __init__(self, model: Model, fast: bool = False, threads: int = 0):
+        self.lib = _load(fast)
+        self.model = model
+        self.n = model.n
+        self._a = a = model.arrays()
+        cm = _CModel()
+        cm.n, cm.nframes = model.n, len(model.fparent)
+        for k in ("parent", "jtype", "fparent"):
+            setattr(cm, k, a[k].ctypes.data_as(_IP))
+        for k in ("Rp", "pp", "mass", "mc", "Io", "arm", "fat", "fR", "fp"):
+            setattr(cm, k, a[k].ctypes.data_as(_DP))
+        cm.grav = (C.c_double * 3)(*model.grav)
+        self._cm = cm
+        self.threads = self.lib.mpcfo_set_threads(int(threads))
+
+    def _ref(self):
+        return C.byref(self._cm)
+
+    def rnea(self, q, qd, qdd=None):
+        n, U = q.shape
+        tau = np.empty((n, U))
+        rc = self.lib.mpcfo_rnea_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                       _p(qdd if qdd is None else _chk(qdd, n, U)), _p(tau))
+        assert rc == 0, rc
+        return tau
+
+    def fk(self, frame: int, q):
+        n, U = q.shape
+        pos, rot = np.empty((3, U)), np.empty((9, U))
+        rc = self.lib.mpcfo_fk_batch(self._ref(), frame, C.c_long(U), _p(_chk(q, n, U)), _p(pos), _p(rot))
+        assert rc == 0, rc
+        return pos, rot
+
+    def jacobian(self, frame: int, q):
+        n, U = q.shape
+        J = np.empty((6 * n, U))
+        rc = self.lib.mpcfo_jac_batch(self._ref(), frame, C.c_long(U), _p(_chk(q, n, U)), _p(J))
+        assert rc == 0, rc
+        return J
+
+    def crba(self, q1):
+        q1 = np.ascontiguousarray(q1, dtype=np.float64)
+        M = np.empty((self.n, self.n))
+        rc = self.lib.mpcfo_crba(self._ref(), _p(q1), _p(M))
+        assert rc == 0, rc
+        return M
+
+    def aba(self, q, qd, tau):
+        n, U = q.shape
+        qdd = np.empty((n, U))
+        rc = self.lib.mpcfo_aba_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                      _p(_chk(tau, n, U)), _p(qdd))
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular (zero joint-space inertia without armature)")
+        return qdd
+
+    def node_eval_ref(self, ee_frames, wsign, q, qd, W, T, h, qdd=None):
+        n, U = q.shape
+        nee = len(ee_frames)
+        fr = (C.c_int * max(nee, 1))(*ee_frames)
+        tau, qn, Tn = np.empty((n, U)), np.empty((n, U)), np.empty((n, U))
+        if W is None:
+            W = np.zeros((6 * max(nee, 1), U))
+        rc = self.lib.mpcfo_node_eval_ref_batch(
+            self._ref(), nee, fr, C.c_double(wsign), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+            _p(qdd), _p(W), _p(T), C.c_double(h), _p(tau), _p(qn), _p(Tn))
+        assert rc == 0, rc
+        return tau, qn, Tn
+
+    def step_rk4(self, q, qd, tau, f, dt, dt_u=None):
+        n, U = q.shape
+        qn, qdn, fn = np.empty((n, U)), np.empty((n, U)), np.empty((n, U))
+        rc = self.lib.mpcfo_step_rk4_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                           _p(_chk(tau, n, U)), _p(_chk(f, n, U)), C.c_double(dt), _p(dt_u),
+                                           _p(qn), _p(qdn), _p(fn))
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular")
+        return qn, qdn, fn
+
+    def step_rk4_jvp(self, q, qd, tau, f, dt, dt_u=None):
+        n, U = q.shape
+        qn, qdn, fn = np.empty((n, U)), np.empty((n, U)), np.empty((n, U))
+        jac = np.empty((3 * n, 4 * n + 1, U))
+        rc = self.lib.mpcfo_step_rk4_jvp_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                               _p(_chk(tau, n, U)), _p(_chk(f, n, U)), C.c_double(dt), _p(dt_u),
+                                               _p(qn), _p(qdn), _p(fn), _p(jac))
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular")
+        return qn, qdn, fn, jac
