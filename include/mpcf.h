@@ -1,0 +1,141 @@
+/*
+ * mpcf.h — C-ABI of the B200-native batched dynamics + fatigue evaluator (libmpcf.so).
+ *
+ * Drop-in boundary for the hot path of ADVRHumanoids/mpc_fatigue.  The reference exposes three
+ * generator functions through pybind11 (bindings/python/pynocchio_casadi.cpp:11-16) that return
+ * serialized CasADi Functions traced from Pinocchio (src/casadi_pinocchio_bridge.hpp:57,87,119).
+ * This library replaces what those Functions *evaluate*, batched over U independent
+ * (scenario, shooting-node) units on one GPU:
+ *
+ *   mpcf_rnea_batch               <- Function "inverse_dynamics"(q,qdot,qddot)->tau   bridge.hpp:57-85
+ *   mpcf_fk_batch                 <- Function "forward_kinematics"(q)->ee_pos,ee_rot   bridge.hpp:87-117
+ *   mpcf_frame_jac_batch          <- Function "jacobian"(q)->J (LOCAL_WORLD_ALIGNED)   bridge.hpp:119-153
+ *   mpcf_node_eval_ref_batch      <- the per-node composition the callers build around them:
+ *                                    tau = ID -/+ J^T W, q+ = q + h qd, T+ = a T + (1-a) Rth P
+ *                                    (python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:290-293,463;
+ *                                     python/Centauro_script/mpc_principal.py:267-301)
+ *   mpcf_aba_batch, mpcf_step_rk4_batch, mpcf_step_rk4_jvp_batch, mpcf_cost_residual_batch
+ *                                 <- north-star additions (forward dynamics, RK4 over (q,qd,f) with
+ *                                    the fatigue compartment ODE, forward-mode Jacobians, per-scenario
+ *                                    cost/residual reduction); no reference code exists for these.
+ *   mpcf_model_create_from_urdf   <- urdf::parseURDF + pinocchio::urdf::buildModel     bridge.hpp:60-63
+ *   mpcf_frame_id                 <- model.getFrameId(body_name)                       bridge.hpp:103
+ *
+ * Conventions
+ *   - every batch array is a raw DEVICE pointer to fp64 data in SoA layout `[component][U]`
+ *     (component-major planes, U contiguous); the library allocates nothing per call;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation;
+ *   - every function returns 0 on success or a negative MPCF_E* code and never throws across the ABI;
+ *     mpcf_last_error() returns a thread-local message for the last failure;
+ *   - a model handle is immutable after creation apart from the two explicit setters, is owned by the
+ *     caller (create/destroy), and may be shared between streams.
+ */
+#ifndef MPCF_H
+#define MPCF_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCF_OK 0
+#define MPCF_EINVAL (-1)     /* bad argument (null pointer, negative size, ...) */
+#define MPCF_EPARSE (-2)     /* malformed URDF */
+#define MPCF_EJOINT (-3)     /* unsupported joint type */
+#define MPCF_EFRAME (-4)     /* unknown frame */
+#define MPCF_ESINGULAR (-5)  /* zero joint-space inertia D_i without armature (forward dynamics) */
+#define MPCF_ECUDA (-6)      /* CUDA runtime error */
+#define MPCF_ELIMIT (-7)     /* model too large for this build (n > MPCF_MAX_DOF) */
+
+#define MPCF_MAX_DOF 64
+#define MPCF_MAX_EE 4
+
+typedef struct mpcf_model mpcf_model;
+
+typedef struct {
+    double armature;    /* rotor inertia added to every joint (reference: 0; config C2: 1e-2) */
+    double gravity[3];  /* default (0, 0, -9.81) */
+    /* fatigue compartment ODE per joint: fdot = -lambda f + kappa (ctau tau^2 + cv qd^2).
+       Defaults are the motor-winding thermal model of python/Libraries/Tmodel_library.py:9-32:
+       lambda = 1/tau_th, kappa = R_th/tau_th, ctau = Ra/ktau^2 (ktau = 40), cv = 1/Rh. */
+    double lambda, kappa, ctau, cv;
+} mpcf_opts;
+
+/* synthetic model kinds */
+#define MPCF_SYNTH_CHAIN 0      /* serial revolute chain of ndof joints */
+#define MPCF_SYNTH_HUMANOID 1   /* floating-base-like branched tree: 3 prismatic + 3 revolute root chain,
+                                   1 torso joint, 2 arms x 7, 4 legs x 4 (37 DOF when ndof = 37) */
+
+void mpcf_opts_default(mpcf_opts *opts);
+
+int mpcf_model_create_from_urdf(const char *xml, size_t len, const mpcf_opts *opts, mpcf_model **out);
+int mpcf_model_create_synthetic(int kind, int ndof, unsigned long long seed, const mpcf_opts *opts,
+                                mpcf_model **out);
+int mpcf_model_destroy(mpcf_model *model);
+int mpcf_model_info(const mpcf_model *model, int *nq, int *nv, int *nbody, int *nframe);
+int mpcf_frame_id(const mpcf_model *model, const char *name);          /* >= 0, or MPCF_EFRAME */
+const char *mpcf_joint_name(const mpcf_model *model, int joint);       /* NULL if out of range */
+const char *mpcf_frame_name(const mpcf_model *model, int frame);
+/* Copy a model array to host memory (tests, input generation).  field is one of:
+   "parent" "jtype" "fparent" (int32) | "Rp" "pp" "mass" "mc" "Io" "arm" "fat" "fR" "fp"
+   "q_lo" "q_hi" "v_max" "tau_max" "grav" (fp64).  Returns bytes written or a negative code. */
+long mpcf_model_export(const mpcf_model *model, const char *field, void *out, size_t cap_bytes);
+int mpcf_model_set_armature(mpcf_model *model, const double *arm /* [n] host */);
+int mpcf_model_set_fatigue(mpcf_model *model, const double *rows /* [n][4] host: lambda kappa ctau cv */);
+/* name of the kernel family a model dispatches to: "chain6", "forest12x6", "generic", ... */
+const char *mpcf_model_kernel_family(const mpcf_model *model);
+
+/* tau[n][U] = RNEA(q, qd, qdd); qdd may be NULL (= 0, as every reference caller passes) */
+int mpcf_rnea_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *qdd,
+                    double *tau, void *stream);
+/* pos[3][U], rot[9][U] (row-major element planes) of frame `frame` */
+int mpcf_fk_batch(const mpcf_model *model, int frame, long U, const double *q, double *pos, double *rot,
+                  void *stream);
+/* J[6*n][U], plane index r*n + i, rows 0-2 linear / 3-5 angular, LOCAL_WORLD_ALIGNED */
+int mpcf_frame_jac_batch(const mpcf_model *model, int frame, long U, const double *q, double *J, void *stream);
+/* out[n][U] = J_frame(q)^T W, W[6][U]  (the fused form every caller actually uses) */
+int mpcf_frame_jac_t_wrench_batch(const mpcf_model *model, int frame, long U, const double *q,
+                                  const double *W, double *out, void *stream);
+/* Reference-mode node evaluation (one launch):
+     tau   = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e      W[6*nee][U]
+     qnext = q + h qd                                        (optional, may be NULL)
+     Tnext = exact zero-order-hold fatigue/thermal map       (optional; needs T)            */
+int mpcf_node_eval_ref_batch(const mpcf_model *model, int nee, const int *ee_frames, double wsign, long U,
+                             const double *q, const double *qd, const double *qdd, const double *W,
+                             const double *T, double h, double *tau, double *qnext, double *Tnext,
+                             void *stream);
+/* qdd[n][U] = forward dynamics(q, qd, tau) */
+int mpcf_aba_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                   double *qdd, void *stream);
+/* One RK4 step of x = (q, qd, f) under xdot = (qd, FD(q,qd,tau), fatigue(f,tau,qd)), tau held.
+   dt_u (per-unit step, [U]) overrides the scalar dt when non-NULL. */
+int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                        const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                        void *stream);
+/* Same plus the dense forward-mode Jacobian jac[3n][4n+1][U]:
+   rows (q+, qd+, f+), columns (q, qd, tau, f, dt).  qn/qdn/fn may be NULL. */
+int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,
+                            const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                            double *qdn, double *fn, double *jac, void *stream);
+/* Per-scenario reduction over the N nodes of each of B scenarios (unit index u = k*B + b):
+     cost[b]      = sum_k  w_qd |qd_k|^2 + w_tau |tau_k|^2
+     resid[0][b]  = max_k |x+_k - x_{k+1}|_inf          multiple-shooting defect (k < N-1)
+     resid[1][b]  = max_k max_i (|tau_ki| - bound_k)+   F0 decaying torque bound
+                    bound_k = max(tau0 exp(-alpha k dt), tau_floor)
+                                                        (python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:136-148)
+     resid[2][b]  = max_k max_i (f+_ki - f_max)+        fatigue / temperature bound
+   out[4][B] = (cost, resid0, resid1, resid2): written directly into the caller's (all-gather send) buffer. */
+int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd,
+                             const double *f, const double *tau, const double *qn, const double *qdn,
+                             const double *fn, double dt, double w_qd, double w_tau, double tau0,
+                             double alpha, double tau_floor, double f_max, double *out, void *stream);
+
+const char *mpcf_last_error(void);
+/* number of kernel launches issued by this library in the calling process since load (bench.py) */
+long mpcf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

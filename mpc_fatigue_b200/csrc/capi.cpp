@@ -1,0 +1,420 @@
+// capi.cpp — the extern "C" boundary of libmpcf.so (see include/mpcf.h for what each entry replaces).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "kernels.cuh"
+#include "model.hpp"
+
+using namespace mpcf;
+
+struct mpcf_model {
+    HostModel h;
+    Family fam = FAM_GENERIC64;
+    // static-family parameter block (largest variant), filled for the family in use
+    StaticParams<12> sp12;
+    StaticParams<6> sp6;
+    StaticParams<3> sp3;
+    // device copy of the generic blob, uploaded lazily on first launch (model creation needs no GPU)
+    mutable std::mutex mu;
+    mutable double *d_dbl = nullptr;
+    mutable int *d_int = nullptr;
+    mutable bool dirty = true;
+    int fd_status = 0;  // 0 unknown, 1 ok, -1 singular
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+extern "C" const char *mpcf_last_error(void) { return g_err.c_str(); }
+extern "C" long mpcf_launch_count(void) { return launch_count(); }
+
+extern "C" void mpcf_opts_default(mpcf_opts *o)
+{
+    if (!o) return;
+    const double Ra = 10.0, Rh = 2.0, Rth = 300.0 * 9.0 / 309.0, Cth = 15.0, ktau = 40.0;
+    const double tth = Rth * Cth;
+    o->armature = 0.0;
+    o->gravity[0] = 0.0; o->gravity[1] = 0.0; o->gravity[2] = -9.81;
+    o->lambda = 1.0 / tth;
+    o->kappa = Rth / tth;
+    o->ctau = Ra / (ktau * ktau);
+    o->cv = 1.0 / Rh;
+}
+
+template <int N>
+static void fill_static(const HostModel &h, StaticParams<N> &p)
+{
+    for (int i = 0; i < N; ++i) {
+        std::memcpy(p.Rp[i], &h.Rp[9 * i], 9 * sizeof(double));
+        std::memcpy(p.pp[i], &h.pp[3 * i], 3 * sizeof(double));
+        p.mass[i] = h.mass[i];
+        std::memcpy(p.mc[i], &h.mc[3 * i], 3 * sizeof(double));
+        std::memcpy(p.Io[i], &h.Io[6 * i], 6 * sizeof(double));
+        p.arm[i] = h.arm[i];
+        std::memcpy(p.fat[i], &h.fat[4 * i], 4 * sizeof(double));
+    }
+    std::memcpy(p.grav, h.grav, sizeof p.grav);
+}
+
+static bool is_forest(const HostModel &h, int L)
+{
+    if (h.n % L) return false;
+    for (int i = 0; i < h.n; ++i) {
+        if (h.jtype[i] != 0) return false;
+        if (h.parent[i] != ((i % L == 0) ? -1 : i - 1)) return false;
+    }
+    return true;
+}
+
+static void refresh(mpcf_model *m)
+{
+    const HostModel &h = m->h;
+    if (h.n == 3 && is_forest(h, 3)) { m->fam = FAM_CHAIN3; fill_static(h, m->sp3); }
+    else if (h.n == 6 && is_forest(h, 6)) { m->fam = FAM_CHAIN6; fill_static(h, m->sp6); }
+    else if (h.n == 12 && is_forest(h, 6)) { m->fam = FAM_FOREST12x6; fill_static(h, m->sp12); }
+    else m->fam = h.n <= 16 ? FAM_GENERIC16 : FAM_GENERIC64;
+    m->dirty = true;
+    m->fd_status = 0;
+}
+
+static int finish_create(mpcf_model *m, int rc, const std::string &err, mpcf_model **out)
+{
+    if (rc != MPCF_OK) {
+        delete m;
+        return fail(rc, err);
+    }
+    refresh(m);
+    *out = m;
+    return MPCF_OK;
+}
+
+extern "C" int mpcf_model_create_from_urdf(const char *xml, size_t len, const mpcf_opts *opts, mpcf_model **out)
+{
+    if (!xml || !out) return fail(MPCF_EINVAL, "null argument");
+    *out = nullptr;
+    mpcf_opts o;
+    if (opts) o = *opts; else mpcf_opts_default(&o);
+    mpcf_model *m = new (std::nothrow) mpcf_model();
+    if (!m) return fail(MPCF_EINVAL, "out of memory");
+    std::string err;
+    int rc;
+    try { rc = parse_urdf(xml, len, o, m->h, err); }
+    catch (const std::exception &e) { rc = MPCF_EPARSE; err = e.what(); }
+    return finish_create(m, rc, err, out);
+}
+
+extern "C" int mpcf_model_create_synthetic(int kind, int ndof, unsigned long long seed, const mpcf_opts *opts, mpcf_model **out)
+{
+    if (!out) return fail(MPCF_EINVAL, "null argument");
+    *out = nullptr;
+    mpcf_opts o;
+    if (opts) o = *opts; else mpcf_opts_default(&o);
+    mpcf_model *m = new (std::nothrow) mpcf_model();
+    if (!m) return fail(MPCF_EINVAL, "out of memory");
+    std::string err;
+    int rc;
+    try { rc = make_synthetic(kind, ndof, seed, o, m->h, err); }
+    catch (const std::exception &e) { rc = MPCF_EINVAL; err = e.what(); }
+    return finish_create(m, rc, err, out);
+}
+
+extern "C" int mpcf_model_destroy(mpcf_model *m)
+{
+    if (!m) return MPCF_OK;
+    if (m->d_dbl) cudaFree(m->d_dbl);
+    if (m->d_int) cudaFree(m->d_int);
+    delete m;
+    return MPCF_OK;
+}
+
+extern "C" int mpcf_model_info(const mpcf_model *m, int *nq, int *nv, int *nbody, int *nframe)
+{
+    if (!m) return fail(MPCF_EINVAL, "null model");
+    if (nq) *nq = m->h.n;
+    if (nv) *nv = m->h.n;
+    if (nbody) *nbody = m->h.n;
+    if (nframe) *nframe = (int)m->h.fparent.size();
+    return MPCF_OK;
+}
+
+extern "C" int mpcf_frame_id(const mpcf_model *m, const char *name)
+{
+    if (!m || !name) return fail(MPCF_EINVAL, "null argument");
+    for (size_t i = 0; i < m->h.frame_names.size(); ++i)
+        if (m->h.frame_names[i] == name) return (int)i;
+    return fail(MPCF_EFRAME, std::string("unknown frame '") + name + "'");
+}
+
+extern "C" const char *mpcf_joint_name(const mpcf_model *m, int j)
+{
+    if (!m || j < 0 || j >= m->h.n) return nullptr;
+    return m->h.joint_names[j].c_str();
+}
+extern "C" const char *mpcf_frame_name(const mpcf_model *m, int f)
+{
+    if (!m || f < 0 || f >= (int)m->h.frame_names.size()) return nullptr;
+    return m->h.frame_names[f].c_str();
+}
+extern "C" const char *mpcf_model_kernel_family(const mpcf_model *m)
+{
+    if (!m) return nullptr;
+    switch (m->fam) {
+    case FAM_CHAIN3: return "chain3";
+    case FAM_CHAIN6: return "chain6";
+    case FAM_FOREST12x6: return "forest12x6";
+    case FAM_GENERIC16: return "generic16";
+    default: return "generic64";
+    }
+}
+
+extern "C" long mpcf_model_export(const mpcf_model *m, const char *field, void *out, size_t cap)
+{
+    if (!m || !field || !out) return fail(MPCF_EINVAL, "null argument");
+    const HostModel &h = m->h;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    std::string f(field);
+    auto dv = [&](const std::vector<double> &v) { src = v.data(); bytes = v.size() * sizeof(double); };
+    auto iv = [&](const std::vector<int> &v) { src = v.data(); bytes = v.size() * sizeof(int); };
+    if (f == "parent") iv(h.parent);
+    else if (f == "jtype") iv(h.jtype);
+    else if (f == "fparent") iv(h.fparent);
+    else if (f == "Rp") dv(h.Rp);
+    else if (f == "pp") dv(h.pp);
+    else if (f == "mass") dv(h.mass);
+    else if (f == "mc") dv(h.mc);
+    else if (f == "Io") dv(h.Io);
+    else if (f == "arm") dv(h.arm);
+    else if (f == "fat") dv(h.fat);
+    else if (f == "fR") dv(h.fR);
+    else if (f == "fp") dv(h.fp);
+    else if (f == "q_lo") dv(h.q_lo);
+    else if (f == "q_hi") dv(h.q_hi);
+    else if (f == "v_max") dv(h.v_max);
+    else if (f == "tau_max") dv(h.tau_max);
+    else if (f == "grav") { src = h.grav; bytes = sizeof h.grav; }
+    else return fail(MPCF_EINVAL, "unknown field '" + f + "'");
+    if (bytes > cap) return fail(MPCF_EINVAL, "buffer too small for field '" + f + "'");
+    std::memcpy(out, src, bytes);
+    return (long)bytes;
+}
+
+extern "C" int mpcf_model_set_armature(mpcf_model *m, const double *arm)
+{
+    if (!m || !arm) return fail(MPCF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (int i = 0; i < m->h.n; ++i) m->h.arm[i] = arm[i];
+    refresh(m);
+    return MPCF_OK;
+}
+extern "C" int mpcf_model_set_fatigue(mpcf_model *m, const double *rows)
+{
+    if (!m || !rows) return fail(MPCF_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (int i = 0; i < 4 * m->h.n; ++i) m->h.fat[i] = rows[i];
+    refresh(m);
+    return MPCF_OK;
+}
+
+// ---- launch plumbing ----
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(MPCF_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
+{
+    const HostModel &h = m->h;
+    lm.fam = m->fam;
+    lm.n = h.n;
+    lm.static_params = nullptr;
+    lm.blob = GenericBlob{nullptr, nullptr, h.n};
+    switch (m->fam) {
+    case FAM_CHAIN3: lm.static_params = &m->sp3; return MPCF_OK;
+    case FAM_CHAIN6: lm.static_params = &m->sp6; return MPCF_OK;
+    case FAM_FOREST12x6: lm.static_params = &m->sp12; return MPCF_OK;
+    default: break;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (m->dirty) {
+        const int n = h.n;
+        std::vector<double> d;
+        d.reserve(blob_doubles(n));
+        auto app = [&](const std::vector<double> &v) { d.insert(d.end(), v.begin(), v.end()); };
+        app(h.Rp); app(h.pp); app(h.mass); app(h.mc); app(h.Io); app(h.arm); app(h.fat);
+        d.insert(d.end(), h.grav, h.grav + 3);
+        std::vector<int> ii(h.parent);
+        ii.insert(ii.end(), h.jtype.begin(), h.jtype.end());
+        cudaError_t e;
+        if (!m->d_dbl && (e = cudaMalloc(&m->d_dbl, d.size() * sizeof(double))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");
+        if (!m->d_int && (e = cudaMalloc(&m->d_int, ii.size() * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");
+        // synchronous copies: the model is immutable afterwards and may be used from any stream
+        if ((e = cudaMemcpy(m->d_dbl, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(model)");
+        if ((e = cudaMemcpy(m->d_int, ii.data(), ii.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(model)");
+        m->dirty = false;
+    }
+    lm.blob.dbl = m->d_dbl;
+    lm.blob.ints = m->d_int;
+    return MPCF_OK;
+}
+
+// Forward dynamics needs D_i = S_i^T IA_i S_i + armature_i > 0.  IA_i >= the composite rigid inertia of the
+// subtree, so check the composite inertia about each joint axis at q = 0 once per model (host, O(n)).
+static int check_forward_dynamics(const mpcf_model *cm)
+{
+    mpcf_model *m = const_cast<mpcf_model *>(cm);
+    if (m->fd_status == 0) {
+        const HostModel &h = m->h;
+        const int n = h.n;
+        std::vector<double> cm_(n), cmc(3 * n), cI(9 * n);
+        for (int i = 0; i < n; ++i) {
+            cm_[i] = h.mass[i];
+            for (int k = 0; k < 3; ++k) cmc[3 * i + k] = h.mc[3 * i + k];
+            const double *o = &h.Io[6 * i];
+            double I[9] = {o[0], o[1], o[2], o[1], o[3], o[4], o[2], o[4], o[5]};
+            std::memcpy(&cI[9 * i], I, sizeof I);
+        }
+        int status = 1;
+        for (int i = n - 1; i >= 0; --i) {
+            const double D = (h.jtype[i] == 0 ? cI[9 * i + 8] : cm_[i]) + h.arm[i];
+            if (!(D > 0.0)) status = -1;
+            const int p = h.parent[i];
+            if (p < 0) continue;
+            const double *R = &h.Rp[9 * i], *t = &h.pp[3 * i];
+            double a[3], RI[9], RIRt[9];
+            for (int r = 0; r < 3; ++r) a[r] = R[3 * r] * cmc[3 * i] + R[3 * r + 1] * cmc[3 * i + 1] + R[3 * r + 2] * cmc[3 * i + 2];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) RI[3 * r + c] = R[3 * r] * cI[9 * i + c] + R[3 * r + 1] * cI[9 * i + 3 + c] + R[3 * r + 2] * cI[9 * i + 6 + c];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) RIRt[3 * r + c] = RI[3 * r] * R[3 * c] + RI[3 * r + 1] * R[3 * c + 1] + RI[3 * r + 2] * R[3 * c + 2];
+            const double ap = a[0] * t[0] + a[1] * t[1] + a[2] * t[2], tt = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+            const double dg = 2 * ap + cm_[i] * tt;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    cI[9 * p + 3 * r + c] += RIRt[3 * r + c] - (a[r] * t[c] + t[r] * a[c] + cm_[i] * t[r] * t[c]) + (r == c ? dg : 0.0);
+            for (int k = 0; k < 3; ++k) cmc[3 * p + k] += a[k] + cm_[i] * t[k];
+            cm_[p] += cm_[i];
+        }
+        m->fd_status = status;
+    }
+    if (m->fd_status < 0)
+        return fail(MPCF_ESINGULAR, "forward dynamics is singular: a joint has zero articulated inertia about its axis; set an armature");
+    return MPCF_OK;
+}
+
+#define PROLOGUE(cond_args)                                              \
+    if (!model) return fail(MPCF_EINVAL, "null model");                  \
+    if (U < 0) return fail(MPCF_EINVAL, "negative batch size");          \
+    if (U > 0 && !(cond_args)) return fail(MPCF_EINVAL, "null array argument"); \
+    LaunchModel lm;                                                      \
+    if (int rc = get_launch_model(model, lm)) return rc;                 \
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+static int frame_arg(const mpcf_model *m, int frame, FrameArg &fa)
+{
+    const HostModel &h = m->h;
+    if (frame < 0 || frame >= (int)h.fparent.size()) return fail(MPCF_EFRAME, "frame index out of range");
+    fa.joint = h.fparent[frame];
+    std::memcpy(fa.R, &h.fR[9 * frame], sizeof fa.R);
+    std::memcpy(fa.p, &h.fp[3 * frame], sizeof fa.p);
+    return MPCF_OK;
+}
+
+static int done(cudaError_t e, const char *what) { return e == cudaSuccess ? MPCF_OK : cuda_fail(e, what); }
+
+extern "C" int mpcf_rnea_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *qdd, double *tau,
+                               void *stream)
+{
+    PROLOGUE(q && qd && tau)
+    return done(launch_rnea(lm, U, q, qd, qdd, tau, st), "rnea_batch");
+}
+
+extern "C" int mpcf_fk_batch(const mpcf_model *model, int frame, long U, const double *q, double *pos, double *rot, void *stream)
+{
+    PROLOGUE(q && pos && rot)
+    FrameArg fa;
+    if (int rc = frame_arg(model, frame, fa)) return rc;
+    return done(launch_fk(lm, fa, U, q, pos, rot, st), "fk_batch");
+}
+
+extern "C" int mpcf_frame_jac_batch(const mpcf_model *model, int frame, long U, const double *q, double *J, void *stream)
+{
+    PROLOGUE(q && J)
+    FrameArg fa;
+    if (int rc = frame_arg(model, frame, fa)) return rc;
+    return done(launch_jac(lm, fa, U, q, J, st), "frame_jac_batch");
+}
+
+extern "C" int mpcf_frame_jac_t_wrench_batch(const mpcf_model *model, int frame, long U, const double *q, const double *W,
+                                             double *out, void *stream)
+{
+    PROLOGUE(q && W && out)
+    EeArgs ee;
+    ee.nee = 1;
+    if (int rc = frame_arg(model, frame, ee.f[0])) return rc;
+    ZohArg zoh{};
+    return done(launch_node_eval(lm, ee, 1.0, U, q, nullptr, nullptr, W, nullptr, 0.0, zoh, out, nullptr, nullptr, true, st),
+                "frame_jac_t_wrench_batch");
+}
+
+extern "C" int mpcf_node_eval_ref_batch(const mpcf_model *model, int nee, const int *ee_frames, double wsign, long U, const double *q,
+                                        const double *qd, const double *qdd, const double *W, const double *T, double h,
+                                        double *tau, double *qnext, double *Tnext, void *stream)
+{
+    PROLOGUE(q && qd && tau)
+    if (nee < 0 || nee > MPCF_MAX_EE) return fail(MPCF_EINVAL, "nee out of range (0..MPCF_MAX_EE)");
+    if (nee > 0 && (!ee_frames || (U > 0 && !W))) return fail(MPCF_EINVAL, "end-effector frames / wrenches missing");
+    if (Tnext && !T && U > 0) return fail(MPCF_EINVAL, "Tnext requested without T");
+    EeArgs ee;
+    ee.nee = nee;
+    for (int e = 0; e < nee; ++e)
+        if (int rc = frame_arg(model, ee_frames[e], ee.f[e])) return rc;
+    ZohArg zoh{};
+    for (int i = 0; i < model->h.n; ++i) zoh.a[i] = std::exp(-model->h.fat[4 * i] * h);
+    return done(launch_node_eval(lm, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, false, st), "node_eval_ref_batch");
+}
+
+extern "C" int mpcf_aba_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau, double *qdd,
+                              void *stream)
+{
+    PROLOGUE(q && qd && tau && qdd)
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_aba(lm, U, q, qd, tau, qdd, st), "aba_batch");
+}
+
+extern "C" int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                                   const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn, void *stream)
+{
+    PROLOGUE(q && qd && tau && f && qn && qdn && fn)
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_step(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, st), "step_rk4_batch");
+}
+
+extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                                       const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                                       double *jac, void *stream)
+{
+    PROLOGUE(q && qd && tau && f && jac)
+    if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
+}
+
+extern "C" int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd, const double *f,
+                                        const double *tau, const double *qn, const double *qdn, const double *fn, double dt,
+                                        double w_qd, double w_tau, double tau0, double alpha, double tau_floor, double f_max,
+                                        double *out, void *stream)
+{
+    if (!model) return fail(MPCF_EINVAL, "null model");
+    if (B < 0 || N <= 0) return fail(MPCF_EINVAL, "bad B / N");
+    if (B > 0 && !(q && qd && f && tau && qn && qdn && fn && out)) return fail(MPCF_EINVAL, "null array argument");
+    CostArgs c{dt, w_qd, w_tau, tau0, alpha, tau_floor, f_max};
+    return done(launch_cost_residual(model->h.n, B, N, q, qd, f, tau, qn, qdn, fn, c, out, static_cast<cudaStream_t>(stream)),
+                "cost_residual_batch");
+}

@@ -1,0 +1,72 @@
+// kernels.cuh — model policies + launcher declarations shared by kernels.cu and capi.cpp
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/mpcf.h"
+
+namespace mpcf {
+
+// ---- compile-time topology: a forest of N/L serial revolute chains of length L ----
+// The constants travel as a __grid_constant__ kernel parameter, i.e. they sit in the constant bank and
+// are consumed directly as DFMA/DMUL operands (no load instruction, no register) once the link loops
+// are fully unrolled.
+template <int N>
+struct StaticParams {
+    double Rp[N][9], pp[N][3], mass[N], mc[N][3], Io[N][6], arm[N], fat[N][4], grav[3];
+};
+
+// ---- run-time topology: model blob staged into shared memory by every block ----
+// blob layout (doubles): Rp 9n | pp 3n | mass n | mc 3n | Io 6n | arm n | fat 4n | grav 3
+// followed by ints: parent n | jtype n
+struct GenericBlob {
+    const double *dbl;  // device
+    const int *ints;    // device
+    int n;
+};
+inline size_t blob_doubles(int n) { return (size_t)27 * n + 3; }
+inline size_t blob_smem_bytes(int n) { return blob_doubles(n) * sizeof(double) + (size_t)2 * n * sizeof(int); }
+
+struct FrameArg {
+    int joint;  // parent joint, -1 = world
+    double R[9], p[3];
+};
+struct EeArgs {
+    int nee;
+    FrameArg f[MPCF_MAX_EE];
+};
+struct ZohArg {
+    double a[MPCF_MAX_DOF];  // exp(-lambda_i h), computed once on the host
+};
+
+enum Family { FAM_GENERIC16 = 0, FAM_GENERIC64, FAM_CHAIN3, FAM_CHAIN6, FAM_FOREST12x6, FAM_COUNT };
+
+struct LaunchModel {
+    Family fam;
+    int n;
+    GenericBlob blob;
+    const void *static_params;  // host pointer to StaticParams<N> for static families
+};
+
+struct CostArgs {
+    double dt, w_qd, w_tau, tau0, alpha, tau_floor, f_max;
+};
+
+// launchers (kernels.cu). All return cudaError_t of the launch.
+cudaError_t launch_rnea(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *tau, cudaStream_t s);
+cudaError_t launch_fk(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *pos, double *rot, cudaStream_t s);
+cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *J, cudaStream_t s);
+cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                             const double *qdd, const double *W, const double *T, double h, const ZohArg &zoh, double *tau,
+                             double *qnext, double *Tnext, bool jtw_only, cudaStream_t s);
+cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *qdd, cudaStream_t s);
+cudaError_t launch_step(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
+                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s);
+cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s);
+cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
+                                 const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,
+                                 cudaStream_t s);
+long launch_count();
+
+}  // namespace mpcf

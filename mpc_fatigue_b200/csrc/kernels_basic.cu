@@ -1,0 +1,209 @@
+// kernels_basic.cu — RNEA, frame FK, frame Jacobian, reference-mode node evaluation, cost/residual reduction.
+#include "launch.cuh"
+
+namespace mpcf {
+
+std::atomic<long> g_launches{0};
+long launch_count() { return g_launches.load(); }
+
+struct RneaBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *qdd, double *tau)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double a[MP::MAXN], b[MP::MAXN], c[MP::MAXN], t[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            a[i] = q[i * U + u];
+            b[i] = qd[i * U + u];
+            c[i] = qdd ? qdd[i * U + u] : 0.0;
+        }
+        Dyn<double, MP>::rnea(m, a, b, c, t);
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) tau[i * U + u] = t[i];
+    }
+};
+
+struct FkBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, FrameArg f, const double *q, double *pos, double *rot)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double a[MP::MAXN], oR[MP::MAXN][9], op[MP::MAXN][3], p[3], R[9];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) a[i] = q[i * U + u];
+        Dyn<double, MP>::fk_all(m, a, oR, op);
+        Dyn<double, MP>::frame_pose(f.joint, f.R, f.p, oR, op, p, R);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pos[k * U + u] = p[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) rot[k * U + u] = R[k];
+    }
+};
+
+// column i of the LOCAL_WORLD_ALIGNED frame Jacobian: [z_i x (p_f - o_i); z_i] (revolute), [z_i; 0] (prismatic)
+template <class MP>
+MPCF_DI void jac_column(const MP &m, int i, double (*oR)[9], double (*op)[3], const double *pf, double *col)
+{
+    const double z[3] = {oR[i][2], oR[i][5], oR[i][8]};
+    if (!m.prismatic(i)) {
+        const double d[3] = {pf[0] - op[i][0], pf[1] - op[i][1], pf[2] - op[i][2]};
+        cross3(z, d, col);
+        col[3] = z[0]; col[4] = z[1]; col[5] = z[2];
+    } else {
+        col[0] = z[0]; col[1] = z[1]; col[2] = z[2];
+        col[3] = 0.0; col[4] = 0.0; col[5] = 0.0;
+    }
+}
+
+struct JacBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, FrameArg f, const double *q, double *J)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double a[MP::MAXN], oR[MP::MAXN][9], op[MP::MAXN][3], p[3], R[9];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) a[i] = q[i * U + u];
+        Dyn<double, MP>::fk_all(m, a, oR, op);
+        Dyn<double, MP>::frame_pose(f.joint, f.R, f.p, oR, op, p, R);
+        int cur = f.joint;
+#pragma unroll UNR
+        for (int i = n - 1; i >= 0; --i) {
+            double col[6] = {0, 0, 0, 0, 0, 0};
+            if (i == cur) {
+                jac_column(m, i, oR, op, p, col);
+                cur = m.parent(i);
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) J[(long)(r * n + i) * U + u] = col[r];
+        }
+    }
+};
+
+// Reference-mode node evaluation, one launch:
+//   tau = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e ; qnext = q + h qd ; Tnext = ZOH(T; tau, qd, h)
+// (python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:290-293,463 ; python/Centauro_script/mpc_principal.py:267-301)
+// jtw_only: skip RNEA and the integrators and write only J^T W (mpcf_frame_jac_t_wrench_batch).
+struct NodeEvalBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, EeArgs ee, double wsign, const double *q, const double *qd,
+                            const double *qdd, const double *W, const double *T, double h, ZohArg zoh, double *tau,
+                            double *qnext, double *Tnext, bool jtw_only)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double a[MP::MAXN], b[MP::MAXN], c[MP::MAXN], t[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            a[i] = q[i * U + u];
+            b[i] = (!jtw_only && qd) ? qd[i * U + u] : 0.0;
+            c[i] = (!jtw_only && qdd) ? qdd[i * U + u] : 0.0;
+            t[i] = 0.0;
+        }
+        if (!jtw_only) Dyn<double, MP>::rnea(m, a, b, c, t);
+        if (ee.nee > 0) {
+            double oR[MP::MAXN][9], op[MP::MAXN][3];
+            Dyn<double, MP>::fk_all(m, a, oR, op);
+            for (int e = 0; e < ee.nee; ++e) {
+                double pf[3], Rf[9], w[6];
+                Dyn<double, MP>::frame_pose(ee.f[e].joint, ee.f[e].R, ee.f[e].p, oR, op, pf, Rf);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) w[r] = W[(long)(6 * e + r) * U + u];
+                int cur = ee.f[e].joint;
+#pragma unroll UNR
+                for (int i = n - 1; i >= 0; --i) {
+                    if (i == cur) {
+                        double col[6];
+                        jac_column(m, i, oR, op, pf, col);
+                        double acc = 0.0;
+#pragma unroll
+                        for (int r = 0; r < 6; ++r) acc += col[r] * w[r];
+                        t[i] += wsign * acc;
+                        cur = m.parent(i);
+                    }
+                }
+            }
+        }
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            tau[i * U + u] = t[i];
+            if (jtw_only) continue;
+            if (qnext) qnext[i * U + u] = a[i] + h * b[i];
+            if (Tnext) {
+                const double P = m.fat(i, 2) * t[i] * t[i] + m.fat(i, 3) * b[i] * b[i];
+                const double Ti = T[i * U + u];
+                const double lam = m.fat(i, 0);
+                Tnext[i * U + u] = (lam == 0.0) ? Ti + h * m.fat(i, 1) * P : zoh.a[i] * Ti + (1.0 - zoh.a[i]) * (m.fat(i, 1) / lam) * P;
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// per-scenario cost / residual reduction: thread b walks the N nodes of scenario b (u = k*B + b,
+// coalesced across b) and writes (cost, defect, torque-bound, fatigue-bound) into out[4][B]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cost_residual_kernel(int n, long B, int N, const double *q, const double *qd, const double *f,
+                                                          const double *tau, const double *qn, const double *qdn, const double *fn,
+                                                          CostArgs c, double *out)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long U = B * N;
+    double cost = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    for (int k = 0; k < N; ++k) {
+        const long u = (long)k * B + b;
+        const double bound = fmax(c.tau0 * exp(-c.alpha * k * c.dt), c.tau_floor);
+        for (int i = 0; i < n; ++i) {
+            const long o = (long)i * U + u;
+            const double v = qd[o], t = tau[o];
+            cost += c.w_qd * v * v + c.w_tau * t * t;
+            r1 = fmax(r1, fabs(t) - bound);
+            r2 = fmax(r2, fn[o] - c.f_max);
+            if (k + 1 < N) {
+                const long o1 = o + B;
+                r0 = fmax(r0, fabs(qn[o] - q[o1]));
+                r0 = fmax(r0, fabs(qdn[o] - qd[o1]));
+                r0 = fmax(r0, fabs(fn[o] - f[o1]));
+            }
+        }
+    }
+    out[b] = cost;
+    out[B + b] = r0;
+    out[2 * B + b] = r1;
+    out[3 * B + b] = r2;
+}
+
+cudaError_t launch_rnea(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *tau, cudaStream_t s)
+{
+    return dispatch<RneaBody>(m, U, 1, s, q, qd, qdd, tau);
+}
+cudaError_t launch_fk(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *pos, double *rot, cudaStream_t s)
+{
+    return dispatch<FkBody>(m, U, 1, s, f, q, pos, rot);
+}
+cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *J, cudaStream_t s)
+{
+    return dispatch<JacBody>(m, U, 1, s, f, q, J);
+}
+cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                             const double *qdd, const double *W, const double *T, double h, const ZohArg &zoh, double *tau,
+                             double *qnext, double *Tnext, bool jtw_only, cudaStream_t s)
+{
+    return dispatch<NodeEvalBody>(m, U, 1, s, ee, wsign, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, jtw_only);
+}
+cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
+                                 const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,
+                                 cudaStream_t s)
+{
+    if (B <= 0) return cudaSuccess;
+    cost_residual_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(n, B, N, q, qd, f, tau, qn, qdn, fn, c, out);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+
+}  // namespace mpcf

@@ -1,0 +1,61 @@
+// kernels_step.cu — forward dynamics and the RK4 step of (q, qd, f) (values only).
+#include "launch.cuh"
+
+namespace mpcf {
+
+struct AbaBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, double *qdd)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double a[MP::MAXN], b[MP::MAXN], c[MP::MAXN], t[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            a[i] = q[i * U + u];
+            b[i] = qd[i * U + u];
+            c[i] = tau[i * U + u];
+        }
+        Dyn<double, MP>::aba(m, a, b, c, t);
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) qdd[i * U + u] = t[i];
+    }
+};
+
+struct StepBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, const double *f,
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        double x[3 * MP::MAXN], t[MP::MAXN], xn[3 * MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            x[i] = q[i * U + u];
+            x[n + i] = qd[i * U + u];
+            x[2 * n + i] = f[i * U + u];
+            t[i] = tau[i * U + u];
+        }
+        const double h = dt_u ? dt_u[u] : dt;
+        Dyn<double, MP>::step_rk4(m, x, t, h, xn);
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            qn[i * U + u] = xn[i];
+            qdn[i * U + u] = xn[n + i];
+            fn[i * U + u] = xn[2 * n + i];
+        }
+    }
+};
+
+cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *qdd, cudaStream_t s)
+{
+    return dispatch<AbaBody>(m, U, 1, s, q, qd, tau, qdd);
+}
+cudaError_t launch_step(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
+                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s)
+{
+    return dispatch<StepBody>(m, U, 1, s, q, qd, tau, f, dt, dt_u, qn, qdn, fn);
+}
+
+}  // namespace mpcf

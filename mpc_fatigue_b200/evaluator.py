@@ -1,0 +1,168 @@
+"""BatchEvaluator: the batched node evaluation that replaces the per-node CasADi calls of the reference
+(python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:259-274 calls `Idyn(q=..,qdot=..,qddot=..)['tau']` once
+per node; here one launch evaluates U = B*N nodes).
+
+All tensors are torch CUDA float64 in the SoA layout of the C-ABI: `[component, U]`, contiguous.
+PyTorch is only the owner of device memory and streams; every operation is a hand-written kernel in
+libmpcf.so launched on `torch.cuda.current_stream()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi
+from .model import Model
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class BatchEvaluator:
+    def __init__(self, model: Model, device: torch.device | str | int | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("mpc_fatigue_b200 needs a CUDA device (there is no CPU fallback)")
+        self.model = model
+        self.n = model.n
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("BatchEvaluator runs on CUDA devices only")
+
+    # ---- argument checking ----
+    def _in(self, t: torch.Tensor | None, rows: int, U: int, name: str, optional: bool = False):
+        if t is None:
+            if optional:
+                return None
+            raise ValueError("%s is required" % name)
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise ValueError("%s must be a contiguous CUDA float64 tensor" % name)
+        if t.device != self.device:
+            raise ValueError("%s is on %s, evaluator is on %s" % (name, t.device, self.device))
+        if tuple(t.shape) != (rows, U):
+            raise ValueError("%s has shape %s, expected (%d, %d)" % (name, tuple(t.shape), rows, U))
+        return C.c_void_p(t.data_ptr())
+
+    def _out(self, t: torch.Tensor | None, rows, U: int, name: str) -> torch.Tensor:
+        shape = tuple(rows) + (U,) if isinstance(rows, tuple) else (rows, U)
+        if t is None:
+            return torch.empty(shape, dtype=torch.float64, device=self.device)
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shape and t.device == self.device):
+            raise ValueError("output %s must be a contiguous CUDA float64 tensor of shape %s" % (name, shape))
+        return t
+
+    @staticmethod
+    def _U(q: torch.Tensor) -> int:
+        if q.dim() != 2:
+            raise ValueError("expected [component, U] tensors")
+        return q.shape[1]
+
+    # ---- the reference's three Functions, batched ----
+    def rnea(self, q, qd, qdd=None, out=None):
+        """tau = inverse_dynamics(q, qdot, qddot)   (bridge.hpp:76-78); qdd=None means zeros."""
+        U, n = self._U(q), self.n
+        tau = self._out(out, n, U, "tau")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_rnea_batch(self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                                                  self._in(qdd, n, U, "qdd", True), C.c_void_p(tau.data_ptr()), _stream()))
+        return tau
+
+    def fk(self, frame: int, q, out_pos=None, out_rot=None):
+        """ee_pos[3,U], ee_rot[9,U] (row-major) = forward_kinematics(q)   (bridge.hpp:106-111)."""
+        U, n = self._U(q), self.n
+        pos, rot = self._out(out_pos, 3, U, "pos"), self._out(out_rot, 9, U, "rot")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_fk_batch(self.model.handle, int(frame), U, self._in(q, n, U, "q"),
+                                                C.c_void_p(pos.data_ptr()), C.c_void_p(rot.data_ptr()), _stream()))
+        return pos, rot
+
+    def jacobian(self, frame: int, q, out=None):
+        """J[6*n,U] (plane r*n+i) = jacobian(q), LOCAL_WORLD_ALIGNED   (bridge.hpp:141-146)."""
+        U, n = self._U(q), self.n
+        J = self._out(out, 6 * n, U, "J")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_frame_jac_batch(self.model.handle, int(frame), U, self._in(q, n, U, "q"),
+                                                       C.c_void_p(J.data_ptr()), _stream()))
+        return J
+
+    def jac_t_wrench(self, frame: int, q, W, out=None):
+        """J(q)^T W without materialising J (what every caller does with the Jacobian)."""
+        U, n = self._U(q), self.n
+        o = self._out(out, n, U, "out")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_frame_jac_t_wrench_batch(self.model.handle, int(frame), U, self._in(q, n, U, "q"),
+                                                                self._in(W, 6, U, "W"), C.c_void_p(o.data_ptr()), _stream()))
+        return o
+
+    def node_eval_ref(self, ee_frames, wsign: float, q, qd, W=None, T=None, h: float = 0.0, qdd=None,
+                      want_qnext=True, want_Tnext=True):
+        """Reference-mode node: tau = RNEA + wsign*sum J^T W, qnext = q + h qd, Tnext = thermal ZOH."""
+        U, n = self._U(q), self.n
+        nee = len(ee_frames)
+        fr = (C.c_int * max(nee, 1))(*[int(f) for f in ee_frames])
+        tau = self._out(None, n, U, "tau")
+        qn = self._out(None, n, U, "qnext") if want_qnext else None
+        Tn = self._out(None, n, U, "Tnext") if (want_Tnext and T is not None) else None
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_node_eval_ref_batch(
+                self.model.handle, nee, fr, float(wsign), U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                self._in(qdd, n, U, "qdd", True), self._in(W, 6 * nee, U, "W", nee == 0), self._in(T, n, U, "T", True),
+                float(h), p(tau), p(qn), p(Tn), _stream()))
+        return tau, qn, Tn
+
+    # ---- north-star additions ----
+    def aba(self, q, qd, tau, out=None):
+        U, n = self._U(q), self.n
+        qdd = self._out(out, n, U, "qdd")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_aba_batch(self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                                                 self._in(tau, n, U, "tau"), C.c_void_p(qdd.data_ptr()), _stream()))
+        return qdd
+
+    def _dt(self, dt, U):
+        if isinstance(dt, torch.Tensor):
+            if not (dt.is_cuda and dt.dtype == torch.float64 and dt.is_contiguous() and tuple(dt.shape) == (U,)):
+                raise ValueError("per-unit dt must be a contiguous CUDA float64 tensor of shape (U,)")
+            return 0.0, C.c_void_p(dt.data_ptr())
+        return float(dt), None
+
+    def step_rk4(self, q, qd, tau, f, dt, out=None):
+        """(q+, qd+, f+) = one RK4 step of (q, qd, f), tau held; dt scalar or per-unit tensor [U]."""
+        U, n = self._U(q), self.n
+        qn, qdn, fn = out if out is not None else (None, None, None)
+        qn, qdn, fn = self._out(qn, n, U, "qn"), self._out(qdn, n, U, "qdn"), self._out(fn, n, U, "fn")
+        dts, dtu = self._dt(dt, U)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_step_rk4_batch(
+                self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(tau, n, U, "tau"),
+                self._in(f, n, U, "f"), dts, dtu, C.c_void_p(qn.data_ptr()), C.c_void_p(qdn.data_ptr()),
+                C.c_void_p(fn.data_ptr()), _stream()))
+        return qn, qdn, fn
+
+    def step_rk4_jvp(self, q, qd, tau, f, dt, out=None, jac=None):
+        """Step plus dense forward-mode Jacobian jac[3n, 4n+1, U]: rows (q+,qd+,f+), cols (q,qd,tau,f,dt)."""
+        U, n = self._U(q), self.n
+        qn, qdn, fn = out if out is not None else (None, None, None)
+        qn, qdn, fn = self._out(qn, n, U, "qn"), self._out(qdn, n, U, "qdn"), self._out(fn, n, U, "fn")
+        jac = self._out(jac, (3 * n, 4 * n + 1), U, "jac")
+        dts, dtu = self._dt(dt, U)
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_step_rk4_jvp_batch(
+                self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(tau, n, U, "tau"),
+                self._in(f, n, U, "f"), dts, dtu, C.c_void_p(qn.data_ptr()), C.c_void_p(qdn.data_ptr()),
+                C.c_void_p(fn.data_ptr()), C.c_void_p(jac.data_ptr()), _stream()))
+        return qn, qdn, fn, jac
+
+    def cost_residual(self, B: int, N: int, q, qd, f, tau, qn, qdn, fn, dt: float, w_qd=1.0, w_tau=1e-2, tau0=50.0,
+                      alpha=2.0, tau_floor=15.0, f_max=80.0, out=None):
+        """Per-scenario (cost, defect, torque-bound, fatigue-bound) -> out[4, B]; units are node-major u = k*B + b."""
+        n, U = self.n, B * N
+        o = self._out(out, 4, B, "out")
+        args = [self._in(t, n, U, nm) for t, nm in ((q, "q"), (qd, "qd"), (f, "f"), (tau, "tau"), (qn, "qn"), (qdn, "qdn"), (fn, "fn"))]
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_cost_residual_batch(self.model.handle, B, N, *args, float(dt), float(w_qd), float(w_tau),
+                                                           float(tau0), float(alpha), float(tau_floor), float(f_max),
+                                                           C.c_void_p(o.data_ptr()), _stream()))
+        return o
