@@ -131,6 +131,17 @@ int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const doubl
                              const double *fn, double dt, double w_qd, double w_tau, double tau0,
                              double alpha, double tau_floor, double f_max, double *out, void *stream);
 
+/* FP64-pipe probe for the roofline denominator: every thread of `blocks` x 256 runs 8 independent DFMA
+   chains for `iters` iterations and writes one double to out[blocks*256] (device).
+   flops = blocks * 256 * iters * 16.  Time it with events on `stream`. */
+int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream);
+
+/* Pitched copy of `height` rows of `width_bytes` between pinned host memory and the device, enqueued on
+   `stream` (kind 1 = host->device, 2 = device->host).  Used by the host-facing pipeline to move the
+   scenario-chunk slice of every SoA plane in one DMA. */
+int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                        size_t height, int kind, void *stream);
+
 const char *mpcf_last_error(void);
 /* number of kernel launches issued by this library in the calling process since load (bench.py) */
 long mpcf_launch_count(void);

@@ -418,3 +418,22 @@ extern "C" int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, 
     return done(launch_cost_residual(model->h.n, B, N, q, qd, f, tau, qn, qdn, fn, c, out, static_cast<cudaStream_t>(stream)),
                 "cost_residual_batch");
 }
+
+extern "C" int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream)
+{
+    if (iters <= 0 || blocks <= 0 || !out) return fail(MPCF_EINVAL, "bad probe arguments");
+    return done(launch_fp64_probe(iters, blocks, out, static_cast<cudaStream_t>(stream)), "probe_fp64");
+}
+
+// Pitched host<->device copies for the host-facing pipeline (scenario-chunk slices of SoA planes).
+// kind: 1 = host->device, 2 = device->host.  Host memory should be pinned for the copy to be asynchronous.
+extern "C" int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t height,
+                                   int kind, void *stream)
+{
+    if (!dst || !src) return fail(MPCF_EINVAL, "null pointer");
+    if (kind != 1 && kind != 2) return fail(MPCF_EINVAL, "kind must be 1 (H2D) or 2 (D2H)");
+    if (width_bytes == 0 || height == 0) return MPCF_OK;
+    return done(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                                  kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
+                "memcpy2d_async");
+}

@@ -67,6 +67,7 @@ cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
                                  const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,
                                  cudaStream_t s);
+cudaError_t launch_fp64_probe(long iters, int blocks, double *out, cudaStream_t s);
 long launch_count();
 
 }  // namespace mpcf

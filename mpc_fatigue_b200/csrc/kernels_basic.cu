@@ -177,6 +177,25 @@ __global__ void __launch_bounds__(256) cost_residual_kernel(int n, long B, int N
     out[3 * B + b] = r2;
 }
 
+// FP64 pipe probe: 8 independent DFMA chains per thread; the roofline denominator of bench.py
+// (MEASURED_PEAKS.json carries no FP64 figure).  flops = blocks * threads * iters * 8 * 2.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(long iters, double *out)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    const double a = 0.999999, b = 1e-7;
+    for (long i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(long)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+cudaError_t launch_fp64_probe(long iters, int blocks, double *out, cudaStream_t s)
+{
+    fp64_probe_kernel<<<blocks, 256, 0, s>>>(iters, out);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rnea(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *tau, cudaStream_t s)
 {
     return dispatch<RneaBody>(m, U, 1, s, q, qd, qdd, tau);
