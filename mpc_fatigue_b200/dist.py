@@ -35,7 +35,7 @@ def allgather_rows(local: torch.Tensor, counts: list[int] | None = None, group=N
     send = local if Bl == Bmax else torch.nn.functional.pad(local, (0, Bmax - Bl))
     send = send.contiguous()
     recv = torch.empty((world, R, Bmax), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(recv, send, group=group)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)  # flat views: accepted by NCCL and gloo alike
     if all(c == Bmax for c in counts):
         return recv.permute(1, 0, 2).reshape(R, world * Bmax)
     return torch.cat([recv[r, :, : counts[r]] for r in range(world)], dim=1)

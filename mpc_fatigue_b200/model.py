@@ -69,7 +69,7 @@ class Model:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _capi is not None and getattr(_capi, "lib", None) is not None:  # module globals vanish at interpreter exit
             _capi.lib.mpcf_model_destroy(h)
 
     # ---- queries ----

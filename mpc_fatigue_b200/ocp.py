@@ -1,0 +1,199 @@
+"""Batched OCP node evaluation — the python/Libraries layer of the reference, re-cut for the GPU evaluator.
+
+The reference builds its NLPs node by node and, after the solve, replays the solution with one CasADi call per
+node and per arm (python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:259-274,
+python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:534-546).  Here one launch evaluates every node of every scenario:
+trajectories are `[B, N, n]` (scenario, node, joint) tensors on the GPU and come back the same way.
+
+  RobotFunctions      InvDyn / ForwKin / Jac wrappers (python/Libraries/Centauro_functions.py:51-78), batched
+  f0_bound_schedule   decaying torque bound  b_k = max(tau0 exp(-alpha k h), floor)
+                      (python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:136-148)
+  step_bound_table    piecewise-constant torque bounds over thirds of the horizon
+                      (python/2_pilz_6_DOF/both_robots_torque_limited_2_pilz.py:129-147)
+  PilzForceOCP        g-rows and cost of the 6-DOF force OCP (force_optimization_pilz_6DOF.py:103-178)
+  DualArmBoxOCP       g-rows of the dual-arm box OCP (Box_Pilz_6DOF2.py:217-475) and the solution.csv layout
+  ThermalMPCNodes     tau / Euler / thermal-ZOH rows of the Centauro thermal MPC (mpc_principal.py:267-327)
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .evaluator import BatchEvaluator
+from .model import Model
+
+
+def _soa(x: torch.Tensor) -> torch.Tensor:
+    """[..., c] -> contiguous [c, U]"""
+    return x.reshape(-1, x.shape[-1]).t().contiguous()
+
+
+def _aos(x: torch.Tensor, batch) -> torch.Tensor:
+    """[c, U] -> [*batch, c]"""
+    return x.t().reshape(*batch, x.shape[0])
+
+
+class RobotFunctions:
+    """Batched equivalents of the L3 wrappers InvDyn / ForwKin* / Jac_* (Centauro_functions.py:51-78)."""
+
+    def __init__(self, urdf: str, device=None, armature: float = 0.0, **model_kw):
+        self.model = Model.from_urdf(urdf, armature=armature, **model_kw)
+        self.ev = BatchEvaluator(self.model, device)
+        self.n = self.model.n
+
+    def InvDyn(self, q, qd, qdd=None):
+        b = q.shape[:-1]
+        return _aos(self.ev.rnea(_soa(q), _soa(qd), None if qdd is None else _soa(qdd)), b)
+
+    def ForwKin(self, frame: str, q):
+        b = q.shape[:-1]
+        pos, rot = self.ev.fk(self.model.frame_id(frame), _soa(q))
+        return _aos(pos, b), _aos(rot, b).reshape(*b, 3, 3)
+
+    def Jac(self, frame: str, q):
+        b = q.shape[:-1]
+        return _aos(self.ev.jacobian(self.model.frame_id(frame), _soa(q)), b).reshape(*b, 6, self.n)
+
+    def joint_torque(self, frame: str, q, qd, W, wsign: float = -1.0, qdd=None):
+        """tau = InvDyn(q, qd, qdd) + wsign * J^T W in one launch (Pilz scripts: wsign=-1, Centauro: +1)."""
+        b = q.shape[:-1]
+        tau, _, _ = self.ev.node_eval_ref([self.model.frame_id(frame)], wsign, _soa(q), _soa(qd), _soa(W), None, 0.0,
+                                          qdd=None if qdd is None else _soa(qdd), want_qnext=False, want_Tnext=False)
+        return _aos(tau, b)
+
+
+def f0_bound_schedule(N: int, h: float, tau0: float = 50.0, alpha: float = 2.0, floor: float = 15.0) -> np.ndarray:
+    """b_k, k = 0..N-1 (force_optimization_pilz_6DOF.py:136-148: exponential decay, floored)."""
+    k = np.arange(N)
+    b = tau0 * np.exp(-alpha * k * h)
+    return np.where(b > floor, b, floor)
+
+
+def step_bound_table(N: int, segments: list[tuple[np.ndarray, np.ndarray]]) -> tuple[np.ndarray, np.ndarray]:
+    """Piecewise-constant [lb, ub] per joint over equal segments of the horizon -> arrays [N, n]
+    (both_robots_torque_limited_2_pilz.py:129-147; Box_Pilz_6DOF2.py:303-433 uses thirds)."""
+    S = len(segments)
+    lb = np.stack([np.asarray(segments[min(S - 1, (k * S) // N)][0], dtype=np.float64) for k in range(N)])
+    ub = np.stack([np.asarray(segments[min(S - 1, (k * S) // N)][1], dtype=np.float64) for k in range(N)])
+    return lb, ub
+
+
+class PilzForceOCP:
+    """Node rows of python/Pilz_6_DOF/force_optimization_pilz_6DOF.py for B scenarios at once.
+
+    decision variables per node: q_k(6), qd_k(6), Fx_k(1); trailing q_N(6)
+    g per node: tau_k(6) in +-b_k ; ee_pos_xy - ref (2) = 0 ; Euler defect (6) = 0 ; cost -= Fx^2
+    """
+
+    def __init__(self, urdf: str, frame: str = "prbt_link_5", N: int = 60, T: float = 2.0, tau0: float = 50.0, alpha: float = 2.0,
+                 floor: float = 15.0, device=None):
+        self.rf = RobotFunctions(urdf, device)
+        self.frame = self.rf.model.frame_id(frame)
+        self.N, self.h = N, T / N
+        self.bound = f0_bound_schedule(N, self.h, tau0, alpha, floor)
+
+    def evaluate(self, q: torch.Tensor, qd: torch.Tensor, Fx: torch.Tensor, ref_xy) -> dict:
+        """q [B, N+1, 6], qd [B, N, 6], Fx [B, N] -> dict of rows."""
+        B, N, n = qd.shape
+        ev = self.rf.ev
+        qk = q[:, :N]
+        W = torch.zeros((B, N, 6), dtype=torch.float64, device=q.device)
+        W[..., 0] = Fx
+        tau, qnext, _ = ev.node_eval_ref([self.frame], -1.0, _soa(qk), _soa(qd), _soa(W), None, self.h, want_Tnext=False)
+        pos, _ = ev.fk(self.frame, _soa(qk))
+        tau = _aos(tau, (B, N))
+        bound = torch.as_tensor(self.bound, dtype=torch.float64, device=q.device).reshape(1, N, 1)
+        return {
+            "tau": tau,
+            "tau_bound": bound.reshape(N),
+            "tau_violation": (tau.abs() - bound).clamp_min(0.0).amax(dim=(1, 2)),
+            "line": _aos(pos, (B, N))[..., :2] - torch.as_tensor(ref_xy, dtype=torch.float64, device=q.device),
+            "defect": _aos(qnext, (B, N)) - q[:, 1:],
+            "cost": -(Fx * Fx).sum(dim=1),
+        }
+
+
+class DualArmBoxOCP:
+    """Dual-arm box OCP (python/2_pilz_6_DOF/Box_Pilz_6DOF2.py): two separate 6-DOF models.
+
+    solution.csv layout (Box_Pilz_6DOF2.py:520-537): per node [q(12), qd(12), F_LR(3), F_RR(3)], then q_N(12).
+    """
+
+    NQ, NF = 12, 3
+
+    def __init__(self, urdf_first: str, urdf_second: str, frame: str = "end_effector", device=None, mass: float = 30.0):
+        self.left = RobotFunctions(urdf_first, device)
+        self.right = RobotFunctions(urdf_second, device)
+        self.fl = self.left.model.frame_id(frame)
+        self.fr = self.right.model.frame_id(frame)
+        self.Fdes = 9.81 * mass  # Box_Pilz_6DOF2.py:197
+
+    @classmethod
+    def parse_solution(cls, vec) -> dict:
+        """solution.csv vector -> q [N+1, 12], qd [N, 12], F_LR [N, 3], F_RR [N, 3]."""
+        v = np.asarray(vec, dtype=np.float64).reshape(-1)
+        stride = 2 * cls.NQ + 2 * cls.NF
+        N, rem = divmod(len(v) - cls.NQ, stride)
+        if rem:
+            raise ValueError("vector length %d is not N*%d+%d" % (len(v), stride, cls.NQ))
+        nodes = v[:N * stride].reshape(N, stride)
+        return {"N": N, "q": np.vstack([nodes[:, :12], v[N * stride:][None]]), "qd": nodes[:, 12:24],
+                "F_LR": nodes[:, 24:27], "F_RR": nodes[:, 27:30]}
+
+    def evaluate(self, q: torch.Tensor, qd: torch.Tensor, F_LR: torch.Tensor, F_RR: torch.Tensor, T: float = 2.0) -> dict:
+        """q [B, N+1, 12], qd [B, N, 12], F_* [B, N, 3] -> constraint rows of Box_Pilz_6DOF2.py:244-293,463-475."""
+        B, N, _ = qd.shape
+        h = T / N
+        z3 = torch.zeros((B, N, 3), dtype=torch.float64, device=q.device)
+        out = {}
+        for side, rf, fr, sl, F in (("L", self.left, self.fl, slice(0, 6), F_LR), ("R", self.right, self.fr, slice(6, 12), F_RR)):
+            qs, qds = q[:, :N, sl], qd[:, :, sl]
+            W = torch.cat([F, z3], dim=-1)
+            tau, qn, _ = rf.ev.node_eval_ref([fr], -1.0, _soa(qs), _soa(qds), _soa(W), None, h, want_Tnext=False)
+            pos, rot = rf.ev.fk(fr, _soa(q[:, :, sl]))
+            out["tau_" + side] = _aos(tau, (B, N))
+            out["defect_" + side] = _aos(qn, (B, N)) - q[:, 1:, sl]
+            out["E_" + side] = _aos(pos, (B, N + 1))
+            out["R_" + side] = _aos(rot, (B, N + 1)).reshape(B, N + 1, 3, 3)
+        E1, E2 = out["E_L"][:, :N], out["E_R"][:, :N]
+        out["force_eq"] = torch.stack([F_LR[..., 2] + F_RR[..., 2] - self.Fdes, F_LR[..., 0] + F_RR[..., 0], F_LR[..., 1] + F_RR[..., 1]], dim=-1)
+        out["moment_eq"] = torch.linalg.cross(E1 - E2, F_LR) + torch.linalg.cross(E2 - E1, F_RR)
+        out["dist2"] = ((E1 - E2) ** 2).sum(-1)
+        return out
+
+
+class ThermalMPCNodes:
+    """tau / Euler / thermal rows of the Centauro thermal MPC node (python/Centauro_script/mpc_principal.py:267-327):
+    tau = InvDyn(q, qd, 0) + sum_e J_e^T W_e ; q_next = q + h qd ; T_next = a T + (1 - a) R_theta P_loss."""
+
+    def __init__(self, model: Model, ee_frames: list[str], T: float = 20.0, N: int = 40, device=None, temperature_bound: float = 80.0):
+        self.model = model
+        self.ev = BatchEvaluator(model, device)
+        self.frames = [model.frame_id(f) for f in ee_frames]
+        self.h = T / N
+        self.N = N
+        self.temperature_bound = temperature_bound  # python/Libraries/MPC_parameters.py:49
+
+    def evaluate(self, q, qd, W, Temp) -> dict:
+        """q [B, N+1, n], qd [B, N, n], W [B, N, 6*nee] (force the robot exerts), Temp [B, N+1, n]."""
+        B, N, n = qd.shape
+        tau, qn, Tn = self.ev.node_eval_ref(self.frames, +1.0, _soa(q[:, :N]), _soa(qd), _soa(W), _soa(Temp[:, :N]), self.h)
+        Tn = _aos(Tn, (B, N))
+        return {"tau": _aos(tau, (B, N)), "q_defect": _aos(qn, (B, N)) - q[:, 1:], "T_defect": Tn - Temp[:, 1:],
+                "T_violation": (Tn - self.temperature_bound).clamp_min(0.0).amax(dim=(1, 2))}
+
+
+def temp_simulation(Ic: float, Tin: float, T: float = 120.0, N: int = 200, Tbound: float = 70.0, ktau: float = 1.0):
+    """Closed-form twin of python/Libraries/TemperatureModel.py:TempSimulation (constant current, zero speed):
+    returns (violated, list of winding temperatures up to the first violation)."""
+    Ra, Rth = 10.0, 300.0 * 9.0 / 309.0
+    tth = Rth * 15.0
+    a = math.e ** (-T / N / tth)
+    Tw = [Tin]
+    for i in range(N):
+        if Tw[i] > Tbound:
+            return True, Tw
+        Tw.append(a * Tw[i] + Ra * Ic * Ic * Rth * (1 - a))
+    return False, Tw[:N]

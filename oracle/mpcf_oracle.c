@@ -202,3 +202,26 @@ int mpcfo_step_rk4_jvp_batch(const mpcfo_model *m, long U, const double *q, cons
     }
     return rc ? -3 : 0;
 }
+
+int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,
+                            double h, double *Tnext)
+{
+    CHECK_N(m);
+    int n = m->n;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u)
+        for (int i = 0; i < n; ++i)
+            Tnext[i * U + u] = fatigue_zoh_r(m, i, T[i * U + u], tau[i * U + u], qd[i * U + u], h);
+    return 0;
+}
+
+int mpcfo_fatigue_rhs_batch(const mpcfo_model *m, long U, const double *f, const double *tau, const double *qd,
+                            double *fdot)
+{
+    CHECK_N(m);
+    int n = m->n;
+    for (long u = 0; u < U; ++u)
+        for (int i = 0; i < n; ++i)
+            fdot[i * U + u] = fatigue_rhs_r(m, i, f[i * U + u], tau[i * U + u], qd[i * U + u]);
+    return 0;
+}

@@ -57,6 +57,12 @@ int mpcfo_step_rk4_jvp_batch(const mpcfo_model *m, long U, const double *q, cons
                              const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                              double *qdn, double *fn, double *jac);
 
+/* exact zero-order-hold fatigue/thermal map and the ODE right-hand side, element-wise per joint */
+int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,
+                            double h, double *Tnext);
+int mpcfo_fatigue_rhs_batch(const mpcfo_model *m, long U, const double *f, const double *tau, const double *qd,
+                            double *fdot);
+
 #ifdef __cplusplus
 }
 #endif

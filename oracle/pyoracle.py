@@ -144,3 +144,19 @@ class Oracle:
         if rc != 0:
             raise ZeroDivisionError("ABA singular")
         return qn, qdn, fn, jac
+
+    def fatigue_zoh(self, T, tau, qd, h):
+        n, U = T.shape
+        out = np.empty((n, U))
+        rc = self.lib.mpcfo_fatigue_zoh_batch(self._ref(), C.c_long(U), _p(_chk(T, n, U)), _p(_chk(tau, n, U)),
+                                              _p(_chk(qd, n, U)), C.c_double(h), _p(out))
+        assert rc == 0, rc
+        return out
+
+    def fatigue_rhs(self, f, tau, qd):
+        n, U = f.shape
+        out = np.empty((n, U))
+        rc = self.lib.mpcfo_fatigue_rhs_batch(self._ref(), C.c_long(U), _p(_chk(f, n, U)), _p(_chk(tau, n, U)),
+                                              _p(_chk(qd, n, U)), _p(out))
+        assert rc == 0, rc
+        return out
