@@ -118,6 +118,21 @@ int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double *q, const 
 int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,
                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                             double *qdn, double *fn, double *jac, void *stream);
+/* Faster Jacobian path for serial-chain models ("chain3", "chain6", "forest12x6"): analytic forward-dynamics
+   derivatives per RK4 stage + a chain rule through the stages, staged through a caller-owned DEVICE workspace.
+   mpcf_step_rk4_jvp_workspace_bytes() returns the size to allocate (bounded: units are processed in chunks),
+   or 0 when the model has no workspace path.  With workspace == NULL (or too small, or such a model) the call
+   falls back to the direct kernel of mpcf_step_rk4_jvp_batch; results agree to rounding. */
+size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, long U);
+int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q, const double *qd,
+                               const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                               double *qdn, double *fn, double *jac, void *workspace, size_t workspace_bytes,
+                               void *stream);
+/* Forward-dynamics derivatives at (q, qd, tau): A = d qdd/d q, B = d qdd/d qd, C = M^-1 = d qdd/d tau,
+   each [n*n][U] with plane index row*n + col. */
+int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                         double *A, double *B, double *C, void *stream);
+
 /* Per-scenario reduction over the N nodes of each of B scenarios (unit index u = k*B + b):
      cost[b]      = sum_k  w_qd |qd_k|^2 + w_tau |tau_k|^2
      resid[0][b]  = max_k |x+_k - x_{k+1}|_inf          multiple-shooting defect (k < N-1)

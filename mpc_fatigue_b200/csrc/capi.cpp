@@ -1,5 +1,6 @@
 // capi.cpp — the extern "C" boundary of libmpcf.so (see include/mpcf.h for what each entry replaces).
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -404,6 +405,43 @@ extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const do
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
     return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
+}
+
+// Workspace of the analytic Jacobian pipeline: (16 n + 12 n^2) doubles per unit, processed in chunks of at most
+// 2^20 units, so the request is bounded (4.4 GB for n = 6) however large U is.
+static const long kJvpChunkUnits = 1L << 20;
+extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, long U)
+{
+    if (!model || U <= 0) return 0;
+    LaunchModel lm;
+    lm.fam = model->fam;
+    if (!jvp2_supported(lm)) return 0;
+    long units = U < kJvpChunkUnits ? U : kJvpChunkUnits;
+    units = (units + 31) / 32 * 32;
+    return (size_t)units * jvp_ws_doubles_per_unit(model->h.n) * sizeof(double);
+}
+
+extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                                          const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                                          double *jac, void *workspace, size_t workspace_bytes, void *stream)
+{
+    PROLOGUE(q && qd && tau && f && jac)
+    if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
+    if (int rc = check_forward_dynamics(model)) return rc;
+    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(model->h.n) * sizeof(double);
+    if (!jvp2_supported(lm) || !workspace || workspace_bytes < min_ws)  // no workspace path: direct dual-number kernel
+        return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
+    if (reinterpret_cast<uintptr_t>(workspace) % 8) return fail(MPCF_EINVAL, "workspace must be 8-byte aligned");
+    return done(launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(workspace), workspace_bytes, st),
+                "step_rk4_jvp_ws_batch");
+}
+
+extern "C" int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau, double *A,
+                                    double *B, double *C, void *stream)
+{
+    PROLOGUE(q && qd && tau && A && B && C)
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_fd_derivs(lm, U, q, qd, tau, A, B, C, st), "fd_derivs_batch");
 }
 
 extern "C" int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd, const double *f,

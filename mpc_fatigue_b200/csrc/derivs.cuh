@@ -1,0 +1,320 @@
+// derivs.cuh — analytic first derivatives of forward dynamics for forests of serial revolute chains:
+//   A = d qdd / d q,  B = d qdd / d qd,  C = M^-1 = d qdd / d tau      (all n x n, block-diagonal per chain)
+// using  d FD/d u = -M^-1 d ID/d u |_(qdd fixed)  and inverse-dynamics derivatives written in WORLD-frame
+// spatial algebra, where no transform appears in the derivative pass:
+//
+//   S_j  = [o_j x z_j ; z_j]                           joint axis as a spatial motion at the world origin
+//   xi_j = S_j x v_p(j)                                (p = parent; v, a are world-frame link velocity / acceleration,
+//   eta_j = S_j x a_p(j) - xi_j x v_p(j)                 a includes the -g base acceleration)
+//   I_c,k, H_c,k, F_c,k, Bs_c,k                        composites over the sub-chain rooted at k of the world-frame rigid
+//                                                      inertia, momentum I v, net force f and the symmetric 3x3
+//                                                      Bs = W + W^T - (h v_l^T + v_l h^T) + 2 (v_l.h) 1,  W = [w]x Io
+//   B_c xi = [-2 H_l x w(xi) ; Bs w(xi) - H_a x w(xi)] (only the angular part w(xi) of xi enters)
+//
+//   dID_m/dq_j  = -S_m . (I_c,m eta_j + B_c,m xi_j)                    m >= j
+//               =  S_m . (S_j x* F_c,j - I_c,j eta_j - B_c,j xi_j)     m <  j
+//   dID_m/dqd_j =  S_m . (B_c,k S_j - 2 I_c,k xi_j),  k = max(m, j)
+//   M_mj        =  S_m . I_c,k S_j (+ armature on the diagonal)
+//
+// Derivation in DESIGN.md §4; checked against complex-step differentiation of the oracle's ABA
+// (tests/test_gpu_parity.py::test_fd_derivs).  There is no reference code for this (north-star addition).
+#pragma once
+
+#include "dyn.cuh"
+
+namespace mpcf {
+
+// spatial motion x motion
+MPCF_DI void mxm(const double *a, const double *b, double *o)
+{
+    double t0[3], t1[3];
+    cross3(a + 3, b, t0);
+    cross3(a, b + 3, t1);
+    cross3(a + 3, b + 3, o + 3);
+    o[0] = t0[0] + t1[0]; o[1] = t0[1] + t1[1]; o[2] = t0[2] + t1[2];
+}
+// spatial motion x* force
+MPCF_DI void mxf(const double *a, const double *f, double *o)
+{
+    double t0[3], t1[3];
+    cross3(a + 3, f, o);
+    cross3(a + 3, f + 3, t0);
+    cross3(a, f, t1);
+    o[3] = t0[0] + t1[0]; o[4] = t0[1] + t1[1]; o[5] = t0[2] + t1[2];
+}
+MPCF_DI double dot6(const double *a, const double *b)
+{
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+MPCF_DI double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+struct RigidInertiaW {  // rigid-body inertia about the world origin, world axes
+    double m, h[3], Io[6];
+    MPCF_DI void apply(const double *x, double *f) const
+    {
+        double t[3], u[3];
+        cross3(h, x + 3, t);
+        cross3(h, x, u);
+        f[0] = m * x[0] - t[0];
+        f[1] = m * x[1] - t[1];
+        f[2] = m * x[2] - t[2];
+        f[3] = Io[0] * x[3] + Io[1] * x[4] + Io[2] * x[5] + u[0];
+        f[4] = Io[1] * x[3] + Io[3] * x[4] + Io[4] * x[5] + u[1];
+        f[5] = Io[2] * x[3] + Io[4] * x[4] + Io[5] * x[5] + u[2];
+    }
+};
+
+// MP must be a static forest policy (kStatic, parent(i) in {i-1, -1}, revolute only).  L = chain length.
+template <class MP, int L>
+struct FdDerivs {
+    static constexpr int N = MP::MAXN;
+
+    struct LinkFwd {
+        double S[6], xi[6], eta[6];  // kept for the pairing pass
+    };
+
+    // A, B, C: row-major [N][N] (entries between different chains are written as 0)
+    static MPCF_DI void run(const MP &m, const double *q, const double *qd, const double *qdd, double *A, double *B, double *C)
+    {
+        LinkFwd K[N];
+        RigidInertiaW Iw[N];
+        double Hw[N][6], Fw[N][6], Bs[N][6];
+        double M[N][N], Dq[N][N], Dv[N][N];
+        double oR[9], o[3], v[6], a[6];
+        // ------------------------------------------------------------------ forward pass (world frame)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool root = m.parent(i) < 0;
+            double s, c;
+            sincos(q[i], &s, &c);
+            double Rl[9], R[9], pos[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Rl[3 * r + 0] = m.Rp(i, 3 * r) * c + m.Rp(i, 3 * r + 1) * s;
+                Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * c - m.Rp(i, 3 * r) * s;
+                Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
+            }
+            if (root) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = Rl[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pos[k] = m.pp(i, k);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { v[k] = 0.0; a[k] = 0.0; }
+                a[0] = -m.grav(0); a[1] = -m.grav(1); a[2] = -m.grav(2);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) R[3 * r + cc] = oR[3 * r] * Rl[cc] + oR[3 * r + 1] * Rl[3 + cc] + oR[3 * r + 2] * Rl[6 + cc];
+                    pos[r] = o[r] + oR[3 * r] * m.pp(i, 0) + oR[3 * r + 1] * m.pp(i, 1) + oR[3 * r + 2] * m.pp(i, 2);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) oR[k] = R[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] = pos[k];
+            LinkFwd &Ki = K[i];
+            const double z[3] = {R[2], R[5], R[8]};
+            cross3(o, z, Ki.S);
+            Ki.S[3] = z[0]; Ki.S[4] = z[1]; Ki.S[5] = z[2];
+            // xi = S x v_parent ; eta = S x a_parent - xi x v_parent   (v, a still hold the parent's values)
+            mxm(Ki.S, v, Ki.xi);
+            double t6[6];
+            mxm(Ki.S, a, Ki.eta);
+            mxm(Ki.xi, v, t6);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Ki.eta[k] -= t6[k];
+            // v_i = v_p + S qd ; a_i = a_p + S qdd - xi qd
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                v[k] += Ki.S[k] * qd[i];
+                a[k] += Ki.S[k] * qdd[i] - Ki.xi[k] * qd[i];
+            }
+            // world-frame rigid inertia of link i
+            RigidInertiaW &I = Iw[i];
+            const double ms = m.mass(i);
+            double a3[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) a3[r] = R[3 * r] * m.mc(i, 0) + R[3 * r + 1] * m.mc(i, 1) + R[3 * r + 2] * m.mc(i, 2);
+            I.m = ms;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) I.h[r] = a3[r] + ms * o[r];
+            {
+                double t[9];  // t = R * Io(local, sym)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double r0 = R[3 * r], r1 = R[3 * r + 1], r2 = R[3 * r + 2];
+                    t[3 * r + 0] = r0 * m.Io(i, 0) + r1 * m.Io(i, 1) + r2 * m.Io(i, 2);
+                    t[3 * r + 1] = r0 * m.Io(i, 1) + r1 * m.Io(i, 3) + r2 * m.Io(i, 4);
+                    t[3 * r + 2] = r0 * m.Io(i, 2) + r1 * m.Io(i, 4) + r2 * m.Io(i, 5);
+                }
+                const int rr[6] = {0, 0, 0, 1, 1, 2}, cc[6] = {0, 1, 2, 1, 2, 2};
+                const double ap = dot3(a3, o), pp = dot3(o, o);
+                const double dg = 2.0 * ap + ms * pp;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int r = rr[k], cI = cc[k];
+                    double e = t[3 * r] * R[3 * cI] + t[3 * r + 1] * R[3 * cI + 1] + t[3 * r + 2] * R[3 * cI + 2];
+                    e -= a3[r] * o[cI] + o[r] * a3[cI] + ms * o[r] * o[cI];
+                    if (r == cI) e += dg;
+                    I.Io[k] = e;
+                }
+            }
+            // momentum, net force, Bs
+            double Ia[6];
+            I.apply(v, Hw[i]);
+            I.apply(a, Ia);
+            mxf(v, Hw[i], Fw[i]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Fw[i][k] += Ia[k];
+            {
+                const double *w = v + 3, *vl = v;
+                // W = [w]x Io ; Bs = W + W^T - (h vl^T + vl h^T) + 2 (vl.h) 1
+                const double Io[3][3] = {{I.Io[0], I.Io[1], I.Io[2]}, {I.Io[1], I.Io[3], I.Io[4]}, {I.Io[2], I.Io[4], I.Io[5]}};
+                double W[3][3];
+#pragma unroll
+                for (int cI = 0; cI < 3; ++cI) {
+                    W[0][cI] = w[1] * Io[2][cI] - w[2] * Io[1][cI];
+                    W[1][cI] = w[2] * Io[0][cI] - w[0] * Io[2][cI];
+                    W[2][cI] = w[0] * Io[1][cI] - w[1] * Io[0][cI];
+                }
+                const double vh2 = 2.0 * dot3(vl, I.h);
+                const int rr[6] = {0, 0, 0, 1, 1, 2}, cc[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int r = rr[k], cI = cc[k];
+                    double e = W[r][cI] + W[cI][r] - (I.h[r] * vl[cI] + vl[r] * I.h[cI]);
+                    if (r == cI) e += vh2;
+                    Bs[i][k] = e;
+                }
+            }
+        }
+        // ------------------------------------------------------------------ composite + pairing pass
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int cI = 0; cI < N; ++cI) { M[r][cI] = 0.0; Dq[r][cI] = 0.0; Dv[r][cI] = 0.0; }
+        RigidInertiaW Ic;
+        double Hc[6], Fc[6], Bc[6];
+#pragma unroll
+        for (int k = N - 1; k >= 0; --k) {
+            const bool leaf = ((k + 1) % L) == 0;
+            const int c0 = (k / L) * L;  // first joint of this chain
+            if (leaf) {
+                Ic = Iw[k];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) { Hc[e] = Hw[k][e]; Fc[e] = Fw[k][e]; Bc[e] = Bs[k][e]; }
+            } else {
+                Ic.m += Iw[k].m;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) Ic.h[e] += Iw[k].h[e];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) { Ic.Io[e] += Iw[k].Io[e]; Hc[e] += Hw[k][e]; Fc[e] += Fw[k][e]; Bc[e] += Bs[k][e]; }
+            }
+            const double *Sk = K[k].S;
+            double rk[6], sk[3];
+            Ic.apply(Sk, rk);
+            {   // s_k = -2 S_l x H_l + Bs S_a - S_a x H_a
+                double t0[3], t1[3];
+                cross3(Sk, Hc, t0);
+                cross3(Sk + 3, Hc + 3, t1);
+                sk[0] = Bc[0] * Sk[3] + Bc[1] * Sk[4] + Bc[2] * Sk[5] - 2.0 * t0[0] - t1[0];
+                sk[1] = Bc[1] * Sk[3] + Bc[3] * Sk[4] + Bc[4] * Sk[5] - 2.0 * t0[1] - t1[1];
+                sk[2] = Bc[2] * Sk[3] + Bc[4] * Sk[4] + Bc[5] * Sk[5] - 2.0 * t0[2] - t1[2];
+            }
+            // g_k = S_k x* F_c - I_c eta_k - B_c xi_k ;  gv_k = B_c S_k - 2 I_c xi_k
+            double gk[6], gvk[6], t6[6], u6[6];
+            mxf(Sk, Fc, gk);
+            Ic.apply(K[k].eta, t6);
+            Ic.apply(K[k].xi, u6);
+            {
+                const double *wx = K[k].xi + 3, *ws = Sk + 3;
+                double bx[6], bs[6], t0[3];
+                cross3(Hc, wx, t0);  // H_l x w
+                bx[0] = -2.0 * t0[0]; bx[1] = -2.0 * t0[1]; bx[2] = -2.0 * t0[2];
+                cross3(Hc + 3, wx, t0);
+                bx[3] = Bc[0] * wx[0] + Bc[1] * wx[1] + Bc[2] * wx[2] - t0[0];
+                bx[4] = Bc[1] * wx[0] + Bc[3] * wx[1] + Bc[4] * wx[2] - t0[1];
+                bx[5] = Bc[2] * wx[0] + Bc[4] * wx[1] + Bc[5] * wx[2] - t0[2];
+                cross3(Hc, ws, t0);
+                bs[0] = -2.0 * t0[0]; bs[1] = -2.0 * t0[1]; bs[2] = -2.0 * t0[2];
+                cross3(Hc + 3, ws, t0);
+                bs[3] = Bc[0] * ws[0] + Bc[1] * ws[1] + Bc[2] * ws[2] - t0[0];
+                bs[4] = Bc[1] * ws[0] + Bc[3] * ws[1] + Bc[4] * ws[2] - t0[1];
+                bs[5] = Bc[2] * ws[0] + Bc[4] * ws[1] + Bc[5] * ws[2] - t0[2];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) {
+                    gk[e] -= t6[e] + bx[e];
+                    gvk[e] = bs[e] - 2.0 * u6[e];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (j < c0 || j > k) continue;  // same chain, j <= k
+                const double mkj = dot6(rk, K[j].S);
+                M[k][j] = mkj;
+                M[j][k] = mkj;
+                Dq[k][j] = -(dot6(rk, K[j].eta) + dot3(sk, K[j].xi + 3));
+                Dv[k][j] = dot3(sk, K[j].S + 3) - 2.0 * dot6(rk, K[j].xi);
+                if (j < k) {
+                    Dq[j][k] = dot6(K[j].S, gk);
+                    Dv[j][k] = dot6(K[j].S, gvk);
+                }
+            }
+            M[k][k] += m.arm(k);
+        }
+        // ------------------------------------------------------------------ per chain: LDL^T, C = M^-1, A = -C Dq, B = -C Dv
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int cI = 0; cI < N; ++cI) { A[r * N + cI] = 0.0; B[r * N + cI] = 0.0; C[r * N + cI] = 0.0; }
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += L) {
+            double Lm[L][L], LD[L][L], Dinv[L];  // LD[i][k] = Lm[i][k] * D[k]
+            // M = Lm D Lm^T, unit lower-triangular Lm
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                double d = M[c0 + j][c0 + j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
+                Dinv[j] = 1.0 / d;
+#pragma unroll
+                for (int i = j + 1; i < L; ++i) {
+                    double e = M[c0 + i][c0 + j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) e -= Lm[i][k] * LD[j][k];
+                    LD[i][j] = e;
+                    Lm[i][j] = e * Dinv[j];
+                }
+            }
+            // solve M x = b for 3 families of right-hand sides
+#pragma unroll
+            for (int col = 0; col < 3 * L; ++col) {
+                double x[L];
+#pragma unroll
+                for (int i = 0; i < L; ++i) {
+                    if (col < L) x[i] = -Dq[c0 + i][c0 + col];
+                    else if (col < 2 * L) x[i] = -Dv[c0 + i][c0 + col - L];
+                    else x[i] = (i == col - 2 * L) ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < L; ++i)
+#pragma unroll
+                    for (int k = 0; k < i; ++k) x[i] -= Lm[i][k] * x[k];
+#pragma unroll
+                for (int i = 0; i < L; ++i) x[i] *= Dinv[i];
+#pragma unroll
+                for (int i = L - 1; i >= 0; --i)
+#pragma unroll
+                    for (int k = i + 1; k < L; ++k) x[i] -= Lm[k][i] * x[k];
+                double *out = col < L ? A : (col < 2 * L ? B : C);
+                const int cj = c0 + col % L;
+#pragma unroll
+                for (int i = 0; i < L; ++i) out[(c0 + i) * N + cj] = x[i];
+            }
+        }
+    }
+};
+
+}  // namespace mpcf

@@ -67,6 +67,14 @@ cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
                                  const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,
                                  cudaStream_t s);
+// analytic Jacobian pipeline (kernels_jvp2.cu): static chain families, caller-provided workspace
+bool jvp2_supported(const LaunchModel &m);
+size_t jvp_ws_doubles_per_unit(int n);
+cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
+                               double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws,
+                               size_t ws_bytes, cudaStream_t s);
+cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
+                             double *C, cudaStream_t s);
 cudaError_t launch_fp64_probe(long iters, int blocks, double *out, cudaStream_t s);
 long launch_count();
 

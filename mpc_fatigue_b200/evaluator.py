@@ -141,18 +141,40 @@ class BatchEvaluator:
                 C.c_void_p(fn.data_ptr()), _stream()))
         return qn, qdn, fn
 
-    def step_rk4_jvp(self, q, qd, tau, f, dt, out=None, jac=None):
-        """Step plus dense forward-mode Jacobian jac[3n, 4n+1, U]: rows (q+,qd+,f+), cols (q,qd,tau,f,dt)."""
+    def fd_derivs(self, q, qd, tau):
+        """A = d qdd/d q, B = d qdd/d qd, C = M^-1 as [n*n, U] planes (row*n + col)."""
+        U, n = self._U(q), self.n
+        A, B, Cm = (self._out(None, n * n, U, nm) for nm in "ABC")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_fd_derivs_batch(self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                                                       self._in(tau, n, U, "tau"), C.c_void_p(A.data_ptr()),
+                                                       C.c_void_p(B.data_ptr()), C.c_void_p(Cm.data_ptr()), _stream()))
+        return A, B, Cm
+
+    def _workspace(self, U: int):
+        """Device workspace of the analytic Jacobian pipeline (cached; bounded by the library's chunking)."""
+        need = int(_capi.lib.mpcf_step_rk4_jvp_workspace_bytes(self.model.handle, U))
+        if need == 0:
+            return None, 0
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() * 8 < need:
+            self._ws = ws = torch.empty(need // 8, dtype=torch.float64, device=self.device)
+        return C.c_void_p(ws.data_ptr()), ws.numel() * 8
+
+    def step_rk4_jvp(self, q, qd, tau, f, dt, out=None, jac=None, direct: bool = False):
+        """Step plus dense forward-mode Jacobian jac[3n, 4n+1, U]: rows (q+,qd+,f+), cols (q,qd,tau,f,dt).
+        Chain models use the analytic workspace pipeline; `direct=True` forces the dual-number kernel."""
         U, n = self._U(q), self.n
         qn, qdn, fn = out if out is not None else (None, None, None)
         qn, qdn, fn = self._out(qn, n, U, "qn"), self._out(qdn, n, U, "qdn"), self._out(fn, n, U, "fn")
         jac = self._out(jac, (3 * n, 4 * n + 1), U, "jac")
         dts, dtu = self._dt(dt, U)
         with torch.cuda.device(self.device):
-            _capi.check(_capi.lib.mpcf_step_rk4_jvp_batch(
+            ws, ws_bytes = (None, 0) if direct else self._workspace(U)
+            _capi.check(_capi.lib.mpcf_step_rk4_jvp_ws_batch(
                 self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(tau, n, U, "tau"),
                 self._in(f, n, U, "f"), dts, dtu, C.c_void_p(qn.data_ptr()), C.c_void_p(qdn.data_ptr()),
-                C.c_void_p(fn.data_ptr()), C.c_void_p(jac.data_ptr()), _stream()))
+                C.c_void_p(fn.data_ptr()), C.c_void_p(jac.data_ptr()), ws, ws_bytes, _stream()))
         return qn, qdn, fn, jac
 
     def cost_residual(self, B: int, N: int, q, qd, f, tau, qn, qdn, fn, dt: float, w_qd=1.0, w_tau=1e-2, tau0=50.0,

@@ -225,3 +225,29 @@ int mpcfo_fatigue_rhs_batch(const mpcfo_model *m, long U, const double *f, const
             fdot[i * U + u] = fatigue_rhs_r(m, i, f[i * U + u], tau[i * U + u], qd[i * U + u]);
     return 0;
 }
+
+/* Forward-dynamics derivatives at (q, qd, tau): A = d qdd/d q, B = d qdd/d qd (complex-step through aba_c),
+ * C = M^-1 = d qdd/d tau.  Outputs are [n*n][U] planes, plane index row*n + col. */
+int mpcfo_fd_derivs_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *tau,
+                          double *A, double *B, double *Cm)
+{
+    CHECK_N(m);
+    const int n = m->n;
+    const double hstep = 1e-40;
+    int rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double complex a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], t[MPCFO_MAXN];
+        for (int d = 0; d < 3 * n; ++d) {
+            for (int i = 0; i < n; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = tau[i * U + u]; }
+            if (d < n) a[d] += hstep * I;
+            else if (d < 2 * n) b[d - n] += hstep * I;
+            else c[d - 2 * n] += hstep * I;
+            rc |= aba_c(m, a, b, c, t) != 0;
+            double *out = d < n ? A : (d < 2 * n ? B : Cm);
+            int col = d % n;
+            for (int r = 0; r < n; ++r) out[((long)r * n + col) * U + u] = cimag(t[r]) / hstep;
+        }
+    }
+    return rc ? -3 : 0;
+}

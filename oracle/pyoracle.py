@@ -160,3 +160,13 @@ class Oracle:
                                               _p(_chk(qd, n, U)), _p(out))
         assert rc == 0, rc
         return out
+
+    def fd_derivs(self, q, qd, tau):
+        """A = d qdd/d q, B = d qdd/d qd, C = M^-1 as [n*n, U] planes (row*n + col)."""
+        n, U = q.shape
+        A, B, Cm = np.empty((n * n, U)), np.empty((n * n, U)), np.empty((n * n, U))
+        rc = self.lib.mpcfo_fd_derivs_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                            _p(_chk(tau, n, U)), _p(A), _p(B), _p(Cm))
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular")
+        return A, B, Cm

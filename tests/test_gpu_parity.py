@@ -115,7 +115,21 @@ def test_step_rk4(setup):
     assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
 
 
-def test_step_rk4_jvp(setup):
+def test_fd_derivs(setup):
+    q, qd, tau, f, qdd = setup["host"]
+    dq, dqd, dtau, df, dqdd = setup["dev"]
+    U = min(setup["U"], 40)
+    sl = lambda a: np.ascontiguousarray(a[:, :U])
+    dsl = lambda a: a[:, :U].contiguous()
+    rA, rB, rC = setup["orc"].fd_derivs(sl(q), sl(qd), sl(tau))
+    gA, gB, gC = setup["ev"].fd_derivs(dsl(dq), dsl(dqd), dsl(dtau))
+    assert rel_err(gC.cpu().numpy(), rC) < TOL
+    assert rel_err(gA.cpu().numpy(), rA) < TOL
+    assert rel_err(gB.cpu().numpy(), rB) < TOL
+
+
+@pytest.mark.parametrize("direct", [False, True], ids=["workspace", "direct"])
+def test_step_rk4_jvp(setup, direct):
     q, qd, tau, f, qdd = setup["host"]
     dq, dqd, dtau, df, dqdd = setup["dev"]
     U = min(setup["U"], 64 if setup["m"].n > 12 else 257)
@@ -123,7 +137,7 @@ def test_step_rk4_jvp(setup):
     dsl = lambda a: a[:, :U].contiguous()
     dt = 0.02
     rq, rqd, rf, rj = setup["orc"].step_rk4_jvp(sl(q), sl(qd), sl(tau), sl(f), dt)
-    gq, gqd, gf, gj = setup["ev"].step_rk4_jvp(dsl(dq), dsl(dqd), dsl(dtau), dsl(df), dt)
+    gq, gqd, gf, gj = setup["ev"].step_rk4_jvp(dsl(dq), dsl(dqd), dsl(dtau), dsl(df), dt, direct=direct)
     assert rel_err_rows(gq.cpu().numpy(), rq) < TOL
     assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL
     assert rel_err_rows(gf.cpu().numpy(), rf) < TOL
