@@ -2,32 +2,49 @@
 // (chain3 / chain6 / forest12x6).  Three kernels per chunk of units, staged through a caller-provided
 // workspace (all planes SoA `[row][chunk]`, coalesced):
 //
-//   K1 step_stages   thread = unit            primal RK4 (ABA) -> x+, and per stage (q_s, qd_s, qdd_s, fdot_s) -> WS1
-//   K2 stage_derivs  thread = (unit, stage)   A_s = dqdd/dq, B_s = dqdd/dqd, C_s = M^-1 (derivs.cuh)        -> WS2
-//   K3 chain_rule    thread = (unit, column)  forward accumulation of d x+/d (q, qd, tau, dt) through the four
-//                                             stages using A_s, B_s, C_s (block = 32 units x all columns, so the
-//                                             columns of one unit share the A/B/C lines through L1)
+//   K1 step_stages   thread = unit            primal RK4 (ABA) -> x+, and per stage (q_s, qd_s, qdd_s, fdot_s) -> workspace
+//   K2 stage_derivs  thread = (unit, stage)   A_s = dqdd/dq, B_s = dqdd/dqd, C_s = M^-1 (derivs.cuh)        -> workspace
+//   K3 chain_rule    warp = (32 units, column) forward accumulation of d x+/d (q, qd, tau, dt) through the four stages.
+//                    Persistent CTAs; one producer thread streams each (tile, stage) chunk of the workspace into a
+//                    shared-memory ring with cp.async.bulk (TMA) + mbarriers; consumer warps read A_s/B_s/C_s from
+//                    shared memory with conflict-free LDS.64 (lane = unit).
+//
+// Workspace layout (AoSoA, tile = 32 units): tile t, stage s -> one contiguous chunk of (3 n^2 + 4 n) planes x 32
+// doubles: first the A, B, C planes (row*n + col), then q_s, qd_s, qdd_s, fdot_s.  Every plane offset inside a chunk is
+// a compile-time constant, so loads/stores carry immediates, and a chunk is a single bulk copy.
 //
 // Cost per unit drops from 19 dual-number sweeps of RK4(ABA) (v1, kernels_jvp.cu) to one primal sweep, four
 // derivative evaluations and 19 cheap column recursions.  Generic (run-time tree) models keep the v1 kernel.
+#include <cstdlib>
+
 #include "derivs.cuh"
 #include "launch.cuh"
 
 namespace mpcf {
 
-static inline size_t ws1_rows(int n) { return (size_t)4 * 4 * n; }
-static inline size_t ws2_rows(int n) { return (size_t)4 * 3 * n * n; }
-size_t jvp_ws_doubles_per_unit(int n) { return ws1_rows(n) + ws2_rows(n); }
+template <int N>
+struct WsLayout {
+    static constexpr int kTile = 32;
+    static constexpr int kPlanes2 = 3 * N * N;                       // A, B, C
+    static constexpr int kPlanes1 = 4 * N;                           // q_s, qd_s, qdd_s, fdot_s
+    static constexpr int kStageDoubles = (kPlanes2 + kPlanes1) * kTile;
+    static constexpr unsigned kStageBytes = kStageDoubles * sizeof(double);
+    static constexpr int kUnitDoubles = 4 * (kPlanes2 + kPlanes1);
+    // chunk of (tile, stage)
+    static MPCF_DI size_t chunk(long tile, int s) { return ((size_t)tile * 4 + s) * kStageDoubles; }
+};
+size_t jvp_ws_doubles_per_unit(int n) { return (size_t)4 * (3 * n * n + 4 * n); }
 
 // ------------------------------------------------------------------------------------------------ K1
 template <int N, int L>
-__global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, long Uc,
+__global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt,
                                                          const double *q, const double *qd, const double *tau, const double *f,
                                                          double dt, const double *dt_u, double *qn, double *qdn, double *fn,
-                                                         double *ws1)
+                                                         double *ws)
 {
     const StaticModel<N, L> m{P};
     using D = Dyn<double, StaticModel<N, L>>;
+    using W = WsLayout<N>;
     const long lu = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (lu >= cnt) return;
     const long u = u0 + lu;
@@ -40,21 +57,22 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
         t[i] = tau[i * U + u];
     }
     const double h = dt_u ? dt_u[u] : dt;
-    const double cs[4] = {0.5, 0.5, 1.0, 0.0}, wt[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
 #pragma unroll
     for (int i = 0; i < 3 * N; ++i) { xs[i] = x[i]; xn[i] = x[i]; }
 #pragma unroll 1
     for (int s = 0; s < 4; ++s) {
+        const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+        const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
         D::xdot(m, xs, t, k);
-        double *w = ws1 + (size_t)s * 4 * N * Uc + lu;
+        double *w = ws + W::chunk(lu / 32, s) + W::kPlanes2 * 32 + (lu & 31);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            w[(size_t)i * Uc] = xs[i];
-            w[(size_t)(N + i) * Uc] = xs[N + i];
-            w[(size_t)(2 * N + i) * Uc] = k[N + i];
-            w[(size_t)(3 * N + i) * Uc] = k[2 * N + i];
+            w[i * 32] = xs[i];
+            w[(N + i) * 32] = xs[N + i];
+            w[(2 * N + i) * 32] = k[N + i];
+            w[(3 * N + i) * 32] = k[2 * N + i];
         }
-        const double a = h * wt[s], c = h * cs[s];
+        const double a = h * wt, c = h * cs;
 #pragma unroll
         for (int i = 0; i < 3 * N; ++i) {
             xn[i] += a * k[i];
@@ -73,32 +91,32 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
 
 // ------------------------------------------------------------------------------------------------ K2
 template <int N, int L>
-__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, long Uc, const double *ws1,
-                                                          double *ws2)
+__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws)
 {
     const StaticModel<N, L> m{P};
+    using W = WsLayout<N>;
     const long lu = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (lu >= cnt) return;
     const int s = blockIdx.y;
-    const double *w = ws1 + (size_t)s * 4 * N * Uc + lu;
+    double *o = ws + W::chunk(lu / 32, s) + (lu & 31);
+    const double *w = o + W::kPlanes2 * 32;
     double q[N], qd[N], qdd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        q[i] = w[(size_t)i * Uc];
-        qd[i] = w[(size_t)(N + i) * Uc];
-        qdd[i] = w[(size_t)(2 * N + i) * Uc];
+        q[i] = w[i * 32];
+        qd[i] = w[(N + i) * 32];
+        qdd[i] = w[(2 * N + i) * 32];
     }
     double A[N * N], B[N * N], C[N * N];
     FdDerivs<StaticModel<N, L>, L>::run(m, q, qd, qdd, A, B, C);
-    double *o = ws2 + (size_t)s * 3 * N * N * Uc + lu;
 #pragma unroll
     for (int r = 0; r < N; ++r)
 #pragma unroll
         for (int c = 0; c < N; ++c) {
             if (r / L != c / L) continue;  // other chains: structurally zero, never read
-            o[(size_t)(r * N + c) * Uc] = A[r * N + c];
-            o[(size_t)(N * N + r * N + c) * Uc] = B[r * N + c];
-            o[(size_t)(2 * N * N + r * N + c) * Uc] = C[r * N + c];
+            o[(r * N + c) * 32] = A[r * N + c];
+            o[(N * N + r * N + c) * 32] = B[r * N + c];
+            o[(2 * N * N + r * N + c) * 32] = C[r * N + c];
         }
 }
 
@@ -150,24 +168,20 @@ struct FdDerivsDualBody {
 
 // ------------------------------------------------------------------------------------------------ K3
 // Column recursion.  With Y_s := dt K_s (+ k_s in the dt column):  X_{s+1} = X_1 + c_s Y_s,  out = X_1 + sum_s w_s Y_s.
+// Per thread: one Jacobian column of one unit = 7 n doubles of state (X, accumulators, new qd-rows).
 template <int N, int L>
-__global__ void __launch_bounds__(32 * (3 * N + 1 > 19 ? 19 : 3 * N + 1))
-    k_chain_rule(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, long Uc, const double *tau, double dt,
-                 const double *dt_u, const double *ws1, const double *ws2, double *jac)
-{
-    const long lu = (long)blockIdx.x * 32 + threadIdx.x;
-    if (lu >= cnt) return;
-    const long u = u0 + lu;
-    const double h = dt_u ? dt_u[u] : dt;
-    constexpr int NC = 3 * N + 1;
-    constexpr long PC = 4 * N + 1;
-    const double cs[4] = {0.5, 0.5, 1.0, 0.0}, wt[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};
-    for (int col = threadIdx.y; col < NC; col += blockDim.y) {
-        const int jq = col < N ? col : -1;                          // q seed
-        const int jv = (col >= N && col < 2 * N) ? col - N : -1;    // qd seed
-        const int jt = (col >= 2 * N && col < 3 * N) ? col - 2 * N : -1;  // tau seed
-        const bool isdt = col == 3 * N;
-        double Xq[N], Xv[N], Xf[N], aq[N], av[N], af[N];
+struct ColumnState {
+    double Xq[N], Xv[N], Xf[N], aq[N], av[N], af[N];
+    int jq, jv, jt;
+    bool isdt;
+    double tauj;
+
+    MPCF_DI void init(int col)
+    {
+        jq = col < N ? col : -1;
+        jv = (col >= N && col < 2 * N) ? col - N : -1;
+        jt = (col >= 2 * N && col < 3 * N) ? col - 2 * N : -1;
+        isdt = col == 3 * N;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             Xq[i] = (i == jq) ? 1.0 : 0.0;
@@ -175,45 +189,53 @@ __global__ void __launch_bounds__(32 * (3 * N + 1 > 19 ? 19 : 3 * N + 1))
             Xf[i] = 0.0;
             aq[i] = Xq[i]; av[i] = Xv[i]; af[i] = 0.0;
         }
-        double tauj = 0.0;
-        if (jt >= 0) tauj = tau[(size_t)jt * U + u];
-#pragma unroll 1
-        for (int s = 0; s < 4; ++s) {
-            const double *w1 = ws1 + (size_t)s * 4 * N * Uc + lu;
-            const double *w2 = ws2 + (size_t)s * 3 * N * N * Uc + lu;
-            double Yq[N], Yv[N], Yf[N];
+    }
+    // one RK4 stage; w points at this lane's element of plane 0 of the (tile, stage) chunk (shared or global memory)
+    MPCF_DI void stage(const StaticParams<N> &P, int s, const double *w, double h)
+    {
+        const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+        const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
+        const double *w1 = w + 3 * N * N * 32;
+        double nv[N];
 #pragma unroll
-            for (int r = 0; r < N; ++r) {
-                double kv = 0.0;
+        for (int r = 0; r < N; ++r) {
+            double kv = 0.0;
+            if (s == 0) {  // X_1 is a unit vector (or zero): the product is a single entry of A_1 / B_1
+                if (jq >= 0 && jq / L == r / L) kv = w[(r * N + jq) * 32];
+                if (jv >= 0 && jv / L == r / L) kv = w[(N * N + r * N + jv) * 32];
+            } else {
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
                     if (r / L != c / L) continue;
-                    kv = fma(w2[(size_t)(r * N + c) * Uc], Xq[c], kv);
-                    kv = fma(w2[(size_t)(N * N + r * N + c) * Uc], Xv[c], kv);
-                }
-                if (jt >= 0 && jt / L == r / L) kv += w2[(size_t)(2 * N * N + r * N + jt) * Uc];
-                const double qds = w1[(size_t)(N + r) * Uc];
-                double kf = 2.0 * P.fat[r][1] * P.fat[r][3] * qds * Xv[r] - P.fat[r][0] * Xf[r];
-                if (r == jt) kf += 2.0 * P.fat[r][1] * P.fat[r][2] * tauj;
-                Yq[r] = h * Xv[r];
-                Yv[r] = h * kv;
-                Yf[r] = h * kf;
-                if (isdt) {
-                    Yq[r] += qds;
-                    Yv[r] += w1[(size_t)(2 * N + r) * Uc];
-                    Yf[r] += w1[(size_t)(3 * N + r) * Uc];
+                    kv = fma(w[(r * N + c) * 32], Xq[c], kv);
+                    kv = fma(w[(N * N + r * N + c) * 32], Xv[c], kv);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                aq[i] = fma(wt[s], Yq[i], aq[i]);
-                av[i] = fma(wt[s], Yv[i], av[i]);
-                af[i] = fma(wt[s], Yf[i], af[i]);
-                Xq[i] = ((i == jq) ? 1.0 : 0.0) + cs[s] * Yq[i];
-                Xv[i] = ((i == jv) ? 1.0 : 0.0) + cs[s] * Yv[i];
-                Xf[i] = cs[s] * Yf[i];
-            }
+            if (jt >= 0 && jt / L == r / L) kv += w[(2 * N * N + r * N + jt) * 32];
+            nv[r] = h * kv;
+            if (isdt) nv[r] += w1[(2 * N + r) * 32];
         }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double qds = w1[(N + i) * 32];
+            double kf = 2.0 * P.fat[i][1] * P.fat[i][3] * qds * Xv[i] - P.fat[i][0] * Xf[i];
+            if (i == jt) kf += 2.0 * P.fat[i][1] * P.fat[i][2] * tauj;
+            double yq = h * Xv[i], yf = h * kf;
+            if (isdt) {
+                yq += qds;
+                yf += w1[(3 * N + i) * 32];
+            }
+            aq[i] = fma(wt, yq, aq[i]);
+            av[i] = fma(wt, nv[i], av[i]);
+            af[i] = fma(wt, yf, af[i]);
+            Xq[i] = ((i == jq) ? 1.0 : 0.0) + cs * yq;
+            Xv[i] = ((i == jv) ? 1.0 : 0.0) + cs * nv[i];
+            Xf[i] = cs * yf;
+        }
+    }
+    MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac) const
+    {
+        constexpr long PC = 4 * N + 1;
         const long ocol = isdt ? 4 * N : col;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -231,22 +253,159 @@ __global__ void __launch_bounds__(32 * (3 * N + 1 > 19 ? 19 : 3 * N + 1))
             }
         }
     }
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.0, sm_90+; forms as in <cuda/ptx>) ----
+MPCF_DI unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+MPCF_DI void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+MPCF_DI void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+MPCF_DI void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.release.cta.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+MPCF_DI void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+MPCF_DI void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Persistent chain-rule kernel for N <= 6: NC consumer warps (one Jacobian column each) + one producer warp.
+template <int N, int L, int NBUF>
+__global__ void __launch_bounds__(32 * (3 * N + 2), 1)
+    k_chain_rule_tma(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac)
+{
+    using W = WsLayout<N>;
+    constexpr int NC = 3 * N + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *buf = reinterpret_cast<double *>(smem_raw);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NBUF * W::kStageBytes);
+    unsigned long long *empty = full + NBUF;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long ntiles = (cnt + 31) / 32;
+    if (warp == NC) {  // ---------------- producer: one thread streams (tile, stage) chunks into the ring
+        if (lane == 0) {
+            unsigned it = 0;
+            for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
+                for (int s = 0; s < 4; ++s, ++it) {
+                    const unsigned slot = it % NBUF, round = it / NBUF;
+                    mbar_wait(&empty[slot], (round & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
+                    bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, s), W::kStageBytes, &full[slot]);
+                }
+        }
+        return;
+    }
+    // ---------------- consumers: warp = column
+    const int col = warp;
+    unsigned it = 0;
+    for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const long lu = t * 32 + lane;
+        const bool live = lu < cnt;
+        const long u = u0 + (live ? lu : 0);
+        const double h = dt_u ? dt_u[u] : dt;
+        ColumnState<N, L> st;
+        st.init(col);
+        st.tauj = st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s, ++it) {
+            const unsigned slot = it % NBUF, round = it / NBUF;
+            mbar_wait(&full[slot], round & 1);
+            st.stage(P, s, buf + (size_t)slot * W::kStageDoubles + lane, h);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+        if (live) st.store(P, col, h, U, u, jac);
+    }
+}
+
+// Fallback for larger models (a stage chunk does not fit the shared-memory ring): same recursion, operands read
+// straight from the workspace tile with immediate plane offsets.
+template <int N, int L, int NCY>
+__global__ void __launch_bounds__(32 * NCY, 2)
+    k_chain_rule_ldg(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac)
+{
+    using W = WsLayout<N>;
+    const long lu = (long)blockIdx.x * 32 + threadIdx.x;
+    if (lu >= cnt) return;
+    const long u = u0 + lu;
+    const double h = dt_u ? dt_u[u] : dt;
+    constexpr int NC = 3 * N + 1;
+    for (int col = threadIdx.y; col < NC; col += blockDim.y) {
+        ColumnState<N, L> st;
+        st.init(col);
+        st.tauj = st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) st.stage(P, s, ws + W::chunk(blockIdx.x, s) + threadIdx.x, h);
+        st.store(P, col, h, U, u, jac);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+static int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int N, int L>
 static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, const double *qd, const double *tau, const double *f,
                             double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws, long Uc,
                             cudaStream_t s)
 {
-    double *ws1 = ws, *ws2 = ws + ws1_rows(N) * (size_t)Uc;
-    constexpr int NCY = 3 * N + 1 > 19 ? 19 : 3 * N + 1;
+    using W = WsLayout<N>;
+    constexpr int NBUF = (N <= 6) ? ((6 * W::kStageBytes + 256 <= 227 * 1024) ? 6 : 4) : 0;
+    constexpr size_t smem = (size_t)NBUF * W::kStageBytes + 2 * NBUF * sizeof(unsigned long long);
+    if constexpr (N <= 6) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+    }
     for (long u0 = 0; u0 < U; u0 += Uc) {
         const long cnt = (U - u0) < Uc ? (U - u0) : Uc;
         const unsigned gb = (unsigned)((cnt + kThreads - 1) / kThreads);
-        k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, Uc, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws1);
-        k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, Uc, ws1, ws2);
-        k_chain_rule<N, L><<<(unsigned)((cnt + 31) / 32), dim3(32, NCY), 0, s>>>(P, U, u0, cnt, Uc, tau, dt, dt_u, ws1, ws2, jac);
+        const long ntiles = (cnt + 31) / 32;
+        k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
+        k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
+        if constexpr (N <= 6) {
+            const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
+            k_chain_rule_tma<N, L, NBUF><<<g3, 32 * (3 * N + 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+        } else {
+            k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+        }
         g_launches.fetch_add(3);
     }
     return cudaGetLastError();
@@ -261,10 +420,8 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
     if (U <= 0) return cudaSuccess;
     const size_t per_unit = jvp_ws_doubles_per_unit(m.n) * sizeof(double);
     long Uc = (long)(ws_bytes / per_unit);
-    if (Uc > U) Uc = U;
-    Uc -= Uc % 32;  // keep every workspace plane 256-byte aligned
-    if (Uc < 32 && U >= 32) return cudaErrorInvalidValue;
-    if (Uc < 32) Uc = 32;
+    Uc -= Uc % 32;  // whole 32-unit tiles
+    if (Uc < 32) return cudaErrorInvalidValue;
     switch (m.fam) {
     case FAM_CHAIN3:
         return run_jvp2<3, 3>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
