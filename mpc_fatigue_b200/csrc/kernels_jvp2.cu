@@ -190,12 +190,33 @@ struct ColumnState {
             aq[i] = Xq[i]; av[i] = Xv[i]; af[i] = 0.0;
         }
     }
-    // one RK4 stage; w points at this lane's element of plane 0 of the (tile, stage) chunk (shared or global memory)
-    MPCF_DI void stage(const StaticParams<N> &P, int s, const double *w, double h)
+    // second half of a stage: fatigue rows, accumulators, next stage state
+    MPCF_DI void finish(const StaticParams<N> &P, int s, const double *w1, double h, const double *nv)
     {
         const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
         const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
-        const double *w1 = w + 3 * N * N * 32;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double qds = w1[(N + i) * 32];
+            double kf = 2.0 * P.fat[i][1] * P.fat[i][3] * qds * Xv[i] - P.fat[i][0] * Xf[i];
+            if (i == jt) kf += 2.0 * P.fat[i][1] * P.fat[i][2] * tauj;
+            double yq = h * Xv[i], yf = h * kf, yv = h * nv[i];
+            if (isdt) {
+                yq += qds;
+                yv += w1[(2 * N + i) * 32];
+                yf += w1[(3 * N + i) * 32];
+            }
+            aq[i] = fma(wt, yq, aq[i]);
+            av[i] = fma(wt, yv, av[i]);
+            af[i] = fma(wt, yf, af[i]);
+            Xq[i] = ((i == jq) ? 1.0 : 0.0) + cs * yq;
+            Xv[i] = ((i == jv) ? 1.0 : 0.0) + cs * yv;
+            Xf[i] = cs * yf;
+        }
+    }
+    // one RK4 stage for ONE column; w points at this lane's element of plane 0 of the (tile, stage) chunk
+    MPCF_DI void stage(const StaticParams<N> &P, int s, const double *w, double h)
+    {
         double nv[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
@@ -212,26 +233,33 @@ struct ColumnState {
                 }
             }
             if (jt >= 0 && jt / L == r / L) kv += w[(2 * N * N + r * N + jt) * 32];
-            nv[r] = h * kv;
-            if (isdt) nv[r] += w1[(2 * N + r) * 32];
+            nv[r] = kv;
         }
+        finish(P, s, w + 3 * N * N * 32, h, nv);
+    }
+    // one RK4 stage for TWO columns of the same unit: every A/B entry is read once and feeds both recursions
+    static MPCF_DI void stage2(ColumnState &a, ColumnState &b, const StaticParams<N> &P, int s, const double *w, double h)
+    {
+        double na[N], nb[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double qds = w1[(N + i) * 32];
-            double kf = 2.0 * P.fat[i][1] * P.fat[i][3] * qds * Xv[i] - P.fat[i][0] * Xf[i];
-            if (i == jt) kf += 2.0 * P.fat[i][1] * P.fat[i][2] * tauj;
-            double yq = h * Xv[i], yf = h * kf;
-            if (isdt) {
-                yq += qds;
-                yf += w1[(3 * N + i) * 32];
+        for (int r = 0; r < N; ++r) {
+            double ka = 0.0, kb = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                if (r / L != c / L) continue;
+                const double A = w[(r * N + c) * 32], B = w[(N * N + r * N + c) * 32];
+                ka = fma(A, a.Xq[c], ka);
+                kb = fma(A, b.Xq[c], kb);
+                ka = fma(B, a.Xv[c], ka);
+                kb = fma(B, b.Xv[c], kb);
             }
-            aq[i] = fma(wt, yq, aq[i]);
-            av[i] = fma(wt, nv[i], av[i]);
-            af[i] = fma(wt, yf, af[i]);
-            Xq[i] = ((i == jq) ? 1.0 : 0.0) + cs * yq;
-            Xv[i] = ((i == jv) ? 1.0 : 0.0) + cs * nv[i];
-            Xf[i] = cs * yf;
+            if (a.jt >= 0 && a.jt / L == r / L) ka += w[(2 * N * N + r * N + a.jt) * 32];
+            if (b.jt >= 0 && b.jt / L == r / L) kb += w[(2 * N * N + r * N + b.jt) * 32];
+            na[r] = ka;
+            nb[r] = kb;
         }
+        a.finish(P, s, w + 3 * N * N * 32, h, na);
+        b.finish(P, s, w + 3 * N * N * 32, h, nb);
     }
     MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac) const
     {
@@ -287,58 +315,69 @@ MPCF_DI void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long 
                  : "memory");
 }
 
-// Persistent chain-rule kernel for N <= 6: NC consumer warps (one Jacobian column each) + one producer warp.
-template <int N, int L, int NBUF>
-__global__ void __launch_bounds__(32 * (3 * N + 2), 1)
+// Persistent chain-rule kernel for N <= 6.  CPW = Jacobian columns per consumer thread (1 or 2); NW consumer warps.
+// No dedicated producer warp: lane 0 of warp 0 refills the ring slot that was released NBUF-1 stages ago before it
+// starts its own stage (the slot is free by then unless the whole CTA is memory-starved).
+template <int N, int L, int NBUF, int CPW>
+__global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
     k_chain_rule_tma(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
                      const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac)
 {
     using W = WsLayout<N>;
     constexpr int NC = 3 * N + 1;
+    constexpr int NW = (NC + CPW - 1) / CPW;  // consumer warps
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NBUF * W::kStageBytes);
     unsigned long long *empty = full + NBUF;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC); }
+    const long ntiles = (cnt + 31) / 32;
+    const long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned nitems = (unsigned)(my_tiles * 4);
+    const bool producer = threadIdx.x == 0;
+    auto issue = [&](unsigned item) {  // item -> (tile, stage) -> ring slot
+        const unsigned slot = item % NBUF, round = item / NBUF;
+        const long t = blockIdx.x + (long)(item / 4) * gridDim.x;
+        mbar_wait(&empty[slot], (round & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
+        bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, item & 3), W::kStageBytes, &full[slot]);
+    };
+    if (producer) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (unsigned i = 0; i < NBUF - 1 && i < nitems; ++i) issue(i);  // prologue: fill all but one slot
     }
     __syncthreads();
-    const long ntiles = (cnt + 31) / 32;
-    if (warp == NC) {  // ---------------- producer: one thread streams (tile, stage) chunks into the ring
-        if (lane == 0) {
-            unsigned it = 0;
-            for (long t = blockIdx.x; t < ntiles; t += gridDim.x)
-                for (int s = 0; s < 4; ++s, ++it) {
-                    const unsigned slot = it % NBUF, round = it / NBUF;
-                    mbar_wait(&empty[slot], (round & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
-                    bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, s), W::kStageBytes, &full[slot]);
-                }
-        }
-        return;
-    }
-    // ---------------- consumers: warp = column
-    const int col = warp;
+    const int col0 = warp, col1 = warp + NW;
+    const bool two = CPW == 2 && col1 < NC;
     unsigned it = 0;
     for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const long lu = t * 32 + lane;
         const bool live = lu < cnt;
         const long u = u0 + (live ? lu : 0);
         const double h = dt_u ? dt_u[u] : dt;
-        ColumnState<N, L> st;
-        st.init(col);
-        st.tauj = st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0;
+        ColumnState<N, L> a, b;
+        a.init(col0);
+        a.tauj = a.jt >= 0 ? tau[(size_t)a.jt * U + u] : 0.0;
+        if (CPW == 2) {
+            b.init(two ? col1 : col0);
+            b.tauj = b.jt >= 0 ? tau[(size_t)b.jt * U + u] : 0.0;
+        }
 #pragma unroll 1
         for (int s = 0; s < 4; ++s, ++it) {
+            if (producer && it + NBUF - 1 < nitems) issue(it + NBUF - 1);
             const unsigned slot = it % NBUF, round = it / NBUF;
             mbar_wait(&full[slot], round & 1);
-            st.stage(P, s, buf + (size_t)slot * W::kStageDoubles + lane, h);
+            const double *w = buf + (size_t)slot * W::kStageDoubles + lane;
+            if (CPW == 2) ColumnState<N, L>::stage2(a, b, P, s, w, h);
+            else a.stage(P, s, w, h);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
         }
-        if (live) st.store(P, col, h, U, u, jac);
+        if (live) {
+            a.store(P, col0, h, U, u, jac);
+            if (two) b.store(P, col1, h, U, u, jac);
+        }
     }
 }
 
@@ -389,7 +428,9 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
     if constexpr (N <= 6) {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
@@ -399,10 +440,14 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         const unsigned gb = (unsigned)((cnt + kThreads - 1) / kThreads);
         const long ntiles = (cnt + 31) / 32;
         k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
-        k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
+        static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 0;
+        if (k2smem > 48 * 1024) cudaFuncSetAttribute(k_stage_derivs<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smem);
+        k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, k2smem, s>>>(P, cnt, ws);
         if constexpr (N <= 6) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
-            k_chain_rule_tma<N, L, NBUF><<<g3, 32 * (3 * N + 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+            static const int cpw = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
+            if (cpw == 2) k_chain_rule_tma<N, L, NBUF, 2><<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+            else k_chain_rule_tma<N, L, NBUF, 1><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
         } else {
             k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
         }
