@@ -74,7 +74,18 @@ struct FdDerivs {
     };
 
     // A, B, C: row-major [N][N] (entries between different chains are written as 0)
+    // convenience wrapper writing row-major [N][N] arrays (entries between different chains are written as 0)
     static MPCF_DI void run(const MP &m, const double *q, const double *qd, const double *qdd, double *A, double *B, double *C)
+    {
+#pragma unroll
+        for (int k = 0; k < N * N; ++k) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
+        run_emit(m, q, qd, qdd, [&](int mat, int r, int c, double v) { (mat == 0 ? A : (mat == 1 ? B : C))[r * N + c] = v; });
+    }
+
+    // emit(mat, row, col, value) is called once for every same-chain entry of A (mat 0), B (1), C (2), column by column,
+    // as soon as the column is solved, so the caller can store it straight to memory instead of holding 3 n^2 values.
+    template <class Emit>
+    static MPCF_DI void run_emit(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit)
     {
         LinkFwd K[N];
         RigidInertiaW Iw[N];
@@ -266,10 +277,6 @@ struct FdDerivs {
         }
         // ------------------------------------------------------------------ per chain: LDL^T, C = M^-1, A = -C Dq, B = -C Dv
 #pragma unroll
-        for (int r = 0; r < N; ++r)
-#pragma unroll
-            for (int cI = 0; cI < N; ++cI) { A[r * N + cI] = 0.0; B[r * N + cI] = 0.0; C[r * N + cI] = 0.0; }
-#pragma unroll
         for (int c0 = 0; c0 < N; c0 += L) {
             double Lm[L][L], LD[L][L], Dinv[L];  // LD[i][k] = Lm[i][k] * D[k]
             // M = Lm D Lm^T, unit lower-triangular Lm
@@ -308,10 +315,9 @@ struct FdDerivs {
                 for (int i = L - 1; i >= 0; --i)
 #pragma unroll
                     for (int k = i + 1; k < L; ++k) x[i] -= Lm[k][i] * x[k];
-                double *out = col < L ? A : (col < 2 * L ? B : C);
                 const int cj = c0 + col % L;
 #pragma unroll
-                for (int i = 0; i < L; ++i) out[(c0 + i) * N + cj] = x[i];
+                for (int i = 0; i < L; ++i) emit(col / L, c0 + i, cj, x[i]);
             }
         }
     }

@@ -67,10 +67,10 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
         double *w = ws + W::chunk(lu / 32, s) + W::kPlanes2 * 32 + (lu & 31);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            w[i * 32] = xs[i];
-            w[(N + i) * 32] = xs[N + i];
-            w[(2 * N + i) * 32] = k[N + i];
-            w[(3 * N + i) * 32] = k[2 * N + i];
+            __stcs(w + i * 32, xs[i]);
+            __stcs(w + (N + i) * 32, xs[N + i]);
+            __stcs(w + (2 * N + i) * 32, k[N + i]);
+            __stcs(w + (3 * N + i) * 32, k[2 * N + i]);
         }
         const double a = h * wt, c = h * cs;
 #pragma unroll
@@ -103,21 +103,12 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
     double q[N], qd[N], qdd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        q[i] = w[i * 32];
-        qd[i] = w[(N + i) * 32];
-        qdd[i] = w[(2 * N + i) * 32];
+        q[i] = __ldcs(w + i * 32);
+        qd[i] = __ldcs(w + (N + i) * 32);
+        qdd[i] = __ldcs(w + (2 * N + i) * 32);
     }
-    double A[N * N], B[N * N], C[N * N];
-    FdDerivs<StaticModel<N, L>, L>::run(m, q, qd, qdd, A, B, C);
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-        for (int c = 0; c < N; ++c) {
-            if (r / L != c / L) continue;  // other chains: structurally zero, never read
-            o[(r * N + c) * 32] = A[r * N + c];
-            o[(N * N + r * N + c) * 32] = B[r * N + c];
-            o[(2 * N * N + r * N + c) * 32] = C[r * N + c];
-        }
+    // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
+    FdDerivs<StaticModel<N, L>, L>::run_emit(m, q, qd, qdd, [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); });
 }
 
 // public fd-derivs entry for static families: thread = unit, qdd from ABA, then the analytic derivatives
@@ -267,9 +258,9 @@ struct ColumnState {
         const long ocol = isdt ? 4 * N : col;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            jac[((size_t)i * PC + ocol) * U + u] = aq[i];
-            jac[((size_t)(N + i) * PC + ocol) * U + u] = av[i];
-            jac[((size_t)(2 * N + i) * PC + ocol) * U + u] = af[i];
+            __stcs(jac + ((size_t)i * PC + ocol) * U + u, aq[i]);
+            __stcs(jac + ((size_t)(N + i) * PC + ocol) * U + u, av[i]);
+            __stcs(jac + ((size_t)(2 * N + i) * PC + ocol) * U + u, af[i]);
         }
         if (isdt) {  // the n fatigue columns in closed form (see kernels_jvp.cu)
 #pragma unroll
@@ -277,7 +268,7 @@ struct ColumnState {
                 const double z = P.fat[j][0] * h;
                 const double g = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
 #pragma unroll
-                for (int r = 0; r < 3 * N; ++r) jac[((size_t)r * PC + 3 * N + j) * U + u] = (r == 2 * N + j) ? g : 0.0;
+                for (int r = 0; r < 3 * N; ++r) __stcs(jac + ((size_t)r * PC + 3 * N + j) * U + u, (r == 2 * N + j) ? g : 0.0);
             }
         }
     }
