@@ -30,6 +30,8 @@ B_PER_GPU = 65536
 DT = 2.0 / N_NODES
 ARMATURE = 1e-2
 NDOF = 6
+# DRAM bytes per unit of the Jacobian pipeline from the committed ncu --set full capture (profiles/); None = not captured
+TRAFFIC_BYTES_PER_UNIT = None
 
 
 # ---- frozen work model (BASELINE.md §3 / SURVEY.md §8d) ----
@@ -241,6 +243,7 @@ def run_gpu(args) -> None:
         time.sleep(0.3)
     launches0 = _capi.lib.mpcf_launch_count()
     pairs = []
+    _capi.lib.mpcf_profile_enable(1)  # per-kernel CUDA events on the launch stream (read after the timed region)
     fence()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -250,6 +253,11 @@ def run_gpu(args) -> None:
     fence()
     launches = _capi.lib.mpcf_launch_count() - launches0
     el_ms = t0.elapsed_time(t1)
+    ms3 = (C.c_double * 3)()
+    nprof = C.c_long()
+    _capi.lib.mpcf_profile_read(ms3, C.byref(nprof))
+    _capi.lib.mpcf_profile_enable(0)
+    kern = {"step_stages": ms3[0] / args.steps, "stage_derivs": ms3[1] / args.steps, "chain_rule": ms3[2] / args.steps}
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([el_ms], dtype=torch.float64, device=dev)
@@ -325,7 +333,13 @@ def run_gpu(args) -> None:
                             "D2H of q+,qd+,f+, dense Jacobian and per-scenario cost/residuals into pinned host staging "
                             "(PCIe-bound: 3.9 KB of Jacobian per unit)"},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": best_tf, "unit": "TFLOP/s", "frac": ach_tf / best_tf,
-                         "traffic": None, "kernel": "step_rk4_jvp (static_kernel<6,6,StepJvpBody>)", "kernel_ms": kern_ms,
+                         "traffic": TRAFFIC_BYTES_PER_UNIT * U if TRAFFIC_BYTES_PER_UNIT else None,
+                         "traffic_source": "profiles/r01_jvp_pipeline.md: dram read+write of the 3 kernels per unit x U (ncu --set full)",
+                         "kernel": "Jacobian pipeline = k_step_stages + k_stage_derivs + k_chain_rule_tma per chunk of 2^20 units",
+                         "kernel_ms": kern_ms, "kernels_ms": kern, "dominant_kernel": max(kern, key=kern.get),
+                         "dominant_share": max(kern.values()) / max(sum(kern.values()), 1e-9),
+                         "note": "frac can exceed 1: the frozen model charges (1 + 25) RK4/ABA sweeps per unit; the analytic "
+                                 "pipeline needs ~6x fewer FP64 instructions (DESIGN.md §5)",
                          "flop_model": "frozen BASELINE.md §3: %d FLOP per unit (values %d x (1 + 25 seeds))" % (fm["step_jac"], fm["step_values"]),
                          "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2)",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

@@ -157,6 +157,12 @@ int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream);
 int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
                         size_t height, int kind, void *stream);
 
+/* Diagnostics: bracket each kernel of the workspace Jacobian pipeline with CUDA events on its launch stream.
+   mpcf_profile_read synchronises and returns accumulated ms of (step_stages, stage_derivs, chain_rule) and the
+   number of timed launches since the last read.  Off by default; single-threaded use only. */
+int mpcf_profile_enable(int on);
+int mpcf_profile_read(double *ms3, long *launches);
+
 const char *mpcf_last_error(void);
 /* number of kernel launches issued by this library in the calling process since load (bench.py) */
 long mpcf_launch_count(void);

@@ -59,6 +59,8 @@ _sig = {
     "mpcf_cost_residual_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int] + [_dp] * 7 + [C.c_double] * 7 + [_dp, C.c_void_p]),
     "mpcf_probe_fp64": (C.c_int, [C.c_long, C.c_int, _dp, C.c_void_p]),
     "mpcf_memcpy2d_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
+    "mpcf_profile_enable": (C.c_int, [C.c_int]),
+    "mpcf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "mpcf_last_error": (C.c_char_p, []),
     "mpcf_launch_count": (C.c_long, []),
 }

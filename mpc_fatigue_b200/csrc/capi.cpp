@@ -475,3 +475,15 @@ extern "C" int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, si
                                   kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
                 "memcpy2d_async");
 }
+
+// Per-kernel timing of the analytic Jacobian pipeline (diagnostics for bench.py; not thread-safe, off by default).
+extern "C" int mpcf_profile_enable(int on)
+{
+    jvp_profile_enable(on != 0);
+    return MPCF_OK;
+}
+extern "C" int mpcf_profile_read(double *ms3, long *launches)
+{
+    if (!ms3 || !launches) return fail(MPCF_EINVAL, "null argument");
+    return jvp_profile_read(ms3, launches);
+}

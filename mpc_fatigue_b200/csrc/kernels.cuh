@@ -75,6 +75,8 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
                                size_t ws_bytes, cudaStream_t s);
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
                              double *C, cudaStream_t s);
+void jvp_profile_enable(bool on);
+int jvp_profile_read(double *ms3, long *launches);
 cudaError_t launch_fp64_probe(long iters, int blocks, double *out, cudaStream_t s);
 long launch_count();
 

@@ -16,6 +16,7 @@
 // Cost per unit drops from 19 dual-number sweeps of RK4(ABA) (v1, kernels_jvp.cu) to one primal sweep, four
 // derivative evaluations and 19 cheap column recursions.  Generic (run-time tree) models keep the v1 kernel.
 #include <cstdlib>
+#include <vector>
 
 #include "derivs.cuh"
 #include "launch.cuh"
@@ -396,6 +397,42 @@ __global__ void __launch_bounds__(32 * NCY, 2)
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// Optional per-kernel timing (bench.py roofline): when enabled, every kernel of the pipeline is bracketed by CUDA
+// events on the launch stream; jvp_profile_read() synchronises and returns the accumulated milliseconds per kernel.
+struct ProfEvent { cudaEvent_t a, b; int k; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof;
+void jvp_profile_enable(bool on) { g_prof_on = on; }
+static void prof_begin(int k, cudaStream_t s)
+{
+    if (!g_prof_on) return;
+    ProfEvent e;
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    e.k = k;
+    cudaEventRecord(e.a, s);
+    g_prof.push_back(e);
+}
+static void prof_end(cudaStream_t s)
+{
+    if (g_prof_on) cudaEventRecord(g_prof.back().b, s);
+}
+int jvp_profile_read(double *ms3, long *launches)
+{
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    *launches = (long)g_prof.size();
+    for (auto &e : g_prof) {
+        float t = 0.f;
+        cudaEventSynchronize(e.b);
+        cudaEventElapsedTime(&t, e.a, e.b);
+        ms3[e.k] += t;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    return 0;
+}
+
 static int sm_count()
 {
     static int n = 0;
@@ -430,10 +467,15 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         const long cnt = (U - u0) < Uc ? (U - u0) : Uc;
         const unsigned gb = (unsigned)((cnt + kThreads - 1) / kThreads);
         const long ntiles = (cnt + 31) / 32;
+        prof_begin(0, s);
         k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
+        prof_end(s);
+        prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 0;
         if (k2smem > 48 * 1024) cudaFuncSetAttribute(k_stage_derivs<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smem);
         k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, k2smem, s>>>(P, cnt, ws);
+        prof_end(s);
+        prof_begin(2, s);
         if constexpr (N <= 6) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
             static const int cpw = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
@@ -442,6 +484,7 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         } else {
             k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
         }
+        prof_end(s);
         g_launches.fetch_add(3);
     }
     return cudaGetLastError();
