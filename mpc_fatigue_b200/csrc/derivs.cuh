@@ -64,14 +64,43 @@ struct RigidInertiaW {  // rigid-body inertia about the world origin, world axes
     }
 };
 
+struct LinkFwd {
+    double S[6], xi[6], eta[6];  // joint axis, xi, eta of one link (world frame): kept for the pairing pass
+};
+template <int N>
+struct LocalLinkStore {
+    LinkFwd K[N];
+    MPCF_DI void put(int i, const LinkFwd &k) { K[i] = k; }
+    MPCF_DI void get(int i, LinkFwd &k) const { k = K[i]; }
+};
+// slab[(i * 18 + e) * stride + tid]: consecutive threads hit consecutive 8-byte words (no bank conflicts)
+struct SharedLinkStore {
+    double *slab;
+    int stride;
+    MPCF_DI void put(int i, const LinkFwd &k)
+    {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+            slab[(i * 18 + e) * stride] = k.S[e];
+            slab[(i * 18 + 6 + e) * stride] = k.xi[e];
+            slab[(i * 18 + 12 + e) * stride] = k.eta[e];
+        }
+    }
+    MPCF_DI void get(int i, LinkFwd &k) const
+    {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+            k.S[e] = slab[(i * 18 + e) * stride];
+            k.xi[e] = slab[(i * 18 + 6 + e) * stride];
+            k.eta[e] = slab[(i * 18 + 12 + e) * stride];
+        }
+    }
+};
+
 // MP must be a static forest policy (kStatic, parent(i) in {i-1, -1}, revolute only).  L = chain length.
 template <class MP, int L>
 struct FdDerivs {
     static constexpr int N = MP::MAXN;
-
-    struct LinkFwd {
-        double S[6], xi[6], eta[6];  // kept for the pairing pass
-    };
 
     // A, B, C: row-major [N][N] (entries between different chains are written as 0)
     // convenience wrapper writing row-major [N][N] arrays (entries between different chains are written as 0)
@@ -87,7 +116,15 @@ struct FdDerivs {
     template <class Emit>
     static MPCF_DI void run_emit(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit)
     {
-        LinkFwd K[N];
+        LocalLinkStore<N> ks;
+        run_emit_ks(m, q, qd, qdd, emit, ks);
+    }
+
+    // KS: where the per-link (S, xi, eta) live between the passes: thread-local arrays (LocalLinkStore) or a
+    // shared-memory slab with a conflict-free [slot][thread] layout (SharedLinkStore).
+    template <class Emit, class KS>
+    static MPCF_DI void run_emit_ks(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit, KS &ks)
+    {
         RigidInertiaW Iw[N];
         double Hw[N][6], Fw[N][6], Bs[N][6];
         double M[N][N], Dq[N][N], Dv[N][N];
@@ -125,7 +162,7 @@ struct FdDerivs {
             for (int k = 0; k < 9; ++k) oR[k] = R[k];
 #pragma unroll
             for (int k = 0; k < 3; ++k) o[k] = pos[k];
-            LinkFwd &Ki = K[i];
+            LinkFwd Ki;
             const double z[3] = {R[2], R[5], R[8]};
             cross3(o, z, Ki.S);
             Ki.S[3] = z[0]; Ki.S[4] = z[1]; Ki.S[5] = z[2];
@@ -142,6 +179,7 @@ struct FdDerivs {
                 v[k] += Ki.S[k] * qd[i];
                 a[k] += Ki.S[k] * qdd[i] - Ki.xi[k] * qd[i];
             }
+            ks.put(i, Ki);
             // world-frame rigid inertia of link i
             RigidInertiaW &I = Iw[i];
             const double ms = m.mass(i);
@@ -223,7 +261,9 @@ struct FdDerivs {
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { Ic.Io[e] += Iw[k].Io[e]; Hc[e] += Hw[k][e]; Fc[e] += Fw[k][e]; Bc[e] += Bs[k][e]; }
             }
-            const double *Sk = K[k].S;
+            LinkFwd Kk;
+            ks.get(k, Kk);
+            const double *Sk = Kk.S;
             double rk[6], sk[3];
             Ic.apply(Sk, rk);
             {   // s_k = -2 S_l x H_l + Bs S_a - S_a x H_a
@@ -237,10 +277,10 @@ struct FdDerivs {
             // g_k = S_k x* F_c - I_c eta_k - B_c xi_k ;  gv_k = B_c S_k - 2 I_c xi_k
             double gk[6], gvk[6], t6[6], u6[6];
             mxf(Sk, Fc, gk);
-            Ic.apply(K[k].eta, t6);
-            Ic.apply(K[k].xi, u6);
+            Ic.apply(Kk.eta, t6);
+            Ic.apply(Kk.xi, u6);
             {
-                const double *wx = K[k].xi + 3, *ws = Sk + 3;
+                const double *wx = Kk.xi + 3, *ws = Sk + 3;
                 double bx[6], bs[6], t0[3];
                 cross3(Hc, wx, t0);  // H_l x w
                 bx[0] = -2.0 * t0[0]; bx[1] = -2.0 * t0[1]; bx[2] = -2.0 * t0[2];
@@ -263,14 +303,16 @@ struct FdDerivs {
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 if (j < c0 || j > k) continue;  // same chain, j <= k
-                const double mkj = dot6(rk, K[j].S);
+                LinkFwd Kj;
+                if (j == k) Kj = Kk; else ks.get(j, Kj);
+                const double mkj = dot6(rk, Kj.S);
                 M[k][j] = mkj;
                 M[j][k] = mkj;
-                Dq[k][j] = -(dot6(rk, K[j].eta) + dot3(sk, K[j].xi + 3));
-                Dv[k][j] = dot3(sk, K[j].S + 3) - 2.0 * dot6(rk, K[j].xi);
+                Dq[k][j] = -(dot6(rk, Kj.eta) + dot3(sk, Kj.xi + 3));
+                Dv[k][j] = dot3(sk, Kj.S + 3) - 2.0 * dot6(rk, Kj.xi);
                 if (j < k) {
-                    Dq[j][k] = dot6(K[j].S, gk);
-                    Dv[j][k] = dot6(K[j].S, gvk);
+                    Dq[j][k] = dot6(Kj.S, gk);
+                    Dv[j][k] = dot6(Kj.S, gvk);
                 }
             }
             M[k][k] += m.arm(k);

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-template <int N, int L>
+template <int N, int L, bool KSMEM>
 __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws)
 {
     const StaticModel<N, L> m{P};
@@ -109,7 +109,14 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
         qdd[i] = __ldcs(w + (2 * N + i) * 32);
     }
     // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
-    FdDerivs<StaticModel<N, L>, L>::run_emit(m, q, qd, qdd, [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); });
+    auto emit = [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); };
+    if (KSMEM) {
+        extern __shared__ double k2_slab[];
+        SharedLinkStore ks{k2_slab + threadIdx.x, (int)blockDim.x};
+        FdDerivs<StaticModel<N, L>, L>::run_emit_ks(m, q, qd, qdd, emit, ks);
+    } else {
+        FdDerivs<StaticModel<N, L>, L>::run_emit(m, q, qd, qdd, emit);
+    }
 }
 
 // public fd-derivs entry for static families: thread = unit, qdd from ABA, then the analytic derivatives
@@ -471,9 +478,15 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
         prof_end(s);
         prof_begin(1, s);
-        static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 0;
-        if (k2smem > 48 * 1024) cudaFuncSetAttribute(k_stage_derivs<N, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2smem);
-        k_stage_derivs<N, L><<<dim3(gb, 4), kThreads, k2smem, s>>>(P, cnt, ws);
+        static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
+        if (k2smem && N <= 6) {  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
+            constexpr int slab = 18 * N * kThreads * (int)sizeof(double);
+            static bool once = false;
+            if (!once) { cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slab); once = true; }
+            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
+        } else {
+            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
+        }
         prof_end(s);
         prof_begin(2, s);
         if constexpr (N <= 6) {
