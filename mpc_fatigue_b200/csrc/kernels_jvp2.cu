@@ -314,6 +314,18 @@ MPCF_DI void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long 
                  : "memory");
 }
 
+// item -> (tile, stage) -> ring slot: wait until the slot is free, arm its `full` barrier, start the bulk copy
+template <class W, int NBUF>
+MPCF_DI void tma_issue(unsigned item, double *buf, unsigned long long *full, unsigned long long *empty, const double *ws, unsigned bid,
+                       unsigned nblk)
+{
+    const unsigned slot = item % NBUF, round = item / NBUF;
+    const long t = bid + (long)(item / 4) * nblk;
+    mbar_wait(&empty[slot], (round & 1) ^ 1);
+    mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
+    bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, item & 3), W::kStageBytes, &full[slot]);
+}
+
 // Persistent chain-rule kernel for N <= 6.  CPW = Jacobian columns per consumer thread (1 or 2); NW consumer warps.
 // No dedicated producer warp: lane 0 of warp 0 refills the ring slot that was released NBUF-1 stages ago before it
 // starts its own stage (the slot is free by then unless the whole CTA is memory-starved).
@@ -334,17 +346,11 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
     const long my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const unsigned nitems = (unsigned)(my_tiles * 4);
     const bool producer = threadIdx.x == 0;
-    auto issue = [&](unsigned item) {  // item -> (tile, stage) -> ring slot
-        const unsigned slot = item % NBUF, round = item / NBUF;
-        const long t = blockIdx.x + (long)(item / 4) * gridDim.x;
-        mbar_wait(&empty[slot], (round & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
-        bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, item & 3), W::kStageBytes, &full[slot]);
-    };
     if (producer) {
         for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (unsigned i = 0; i < NBUF - 1 && i < nitems; ++i) issue(i);  // prologue: fill all but one slot
+        for (unsigned i = 0; i < NBUF - 1 && i < nitems; ++i)  // prologue: fill all but one slot
+            tma_issue<W, NBUF>(i, buf, full, empty, ws, blockIdx.x, gridDim.x);
     }
     __syncthreads();
     const int col0 = warp, col1 = warp + NW;
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
         }
 #pragma unroll 1
         for (int s = 0; s < 4; ++s, ++it) {
-            if (producer && it + NBUF - 1 < nitems) issue(it + NBUF - 1);
+            if (producer && it + NBUF - 1 < nitems) tma_issue<W, NBUF>(it + NBUF - 1, buf, full, empty, ws, blockIdx.x, gridDim.x);
             const unsigned slot = it % NBUF, round = it / NBUF;
             mbar_wait(&full[slot], round & 1);
             const double *w = buf + (size_t)slot * W::kStageDoubles + lane;
