@@ -549,12 +549,162 @@ struct Dyn {
         return m.fat(i, 1) * (m.fat(i, 2) * (tau * tau) + m.fat(i, 3) * (qd * qd)) - m.fat(i, 0) * f;
     }
 
+    // =========================================================================================
+    // Forward dynamics through the joint-space inertia matrix: qdd = M^-1 (tau - h).
+    // One fused sweep pair computes the RNEA bias h = ID(q, qd, 0) and, from the composite rigid-body inertias,
+    // the columns of M (CRBA); M is factorised M = L D L^T in place.  For short chains (n <~ 9) this is cheaper than ABA
+    // (no 6x6 articulated inertias to carry and transform).  Static forests of revolute chains only (parent = i - 1).
+    // =========================================================================================
+    template <int L>
+    static MPCF_DI bool fd_crba(const MP &m, const T *q, const T *qd, const T *tau, T *qdd)
+    {
+        static_assert(MP::kStatic, "fd_crba needs a compile-time forest of chains");
+        constexpr int N = MAXN;
+        JointVar<T> jv[N];
+        T f[N][6];
+        T Mx[N][L];  // M[i][j] stored as Mx[i][j - c0], same chain only
+        T h[N];
+        {   // pass 1: velocities, bias accelerations (qdd = 0), link forces
+            T v[6], a[6];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const bool root = m.parent(i) < 0;
+                joint_var(m, i, q[i], jv[i]);
+                T vp[6], ap[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { vp[k] = root ? T(0.0) : v[k]; ap[k] = root ? T(0.0) : a[k]; }
+                if (root) { ap[0] = T(-m.grav(0)); ap[1] = T(-m.grav(1)); ap[2] = T(-m.grav(2)); }
+                motion_to_child(m, i, jv[i], vp, v);
+                v[5] += qd[i];
+                motion_to_child(m, i, jv[i], ap, a);
+                T c[6];
+                bias_c(m, i, v, qd[i], c);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a[k] += c[k];
+                T hv[6], fa[6], fb[6];
+                inertia_mul(m, i, v, hv);
+                inertia_mul(m, i, a, fa);
+                crossf(v, hv, fb);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) f[i][k] = fa[k] + fb[k];
+            }
+        }
+        {   // pass 2: bias torques, composite inertias (mass, mass*com, inertia about the joint origin), columns of M
+            T cm, cmc[3], cI[6];
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) {
+                const bool leaf = ((i + 1) % L) == 0;
+                const int c0 = (i / L) * L;
+                if (leaf) {
+                    cm = T(m.mass(i));
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cmc[k] = T(m.mc(i, k));
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) cI[k] = T(m.Io(i, k));
+                } else {
+                    cm += m.mass(i);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cmc[k] += m.mc(i, k);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) cI[k] += m.Io(i, k);
+                }
+                h[i] = f[i][5];
+                // column i of M: F = Yc_i S (S = e5) = [-(mc x z); Io[:, 2]], then carried up the chain
+                T F[6] = {-cmc[1], cmc[0], T(0.0), cI[2], cI[4], cI[5]};
+                Mx[i][i - c0] = F[5] + m.arm(i);
+#pragma unroll
+                for (int j = i; j > c0; --j) {
+                    T Fp[6];
+                    force_to_parent(m, j, jv[j], F, Fp);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) F[k] = Fp[k];
+                    Mx[i][j - 1 - c0] = F[5];
+                }
+                if (i > c0) {
+                    // bias force and composite inertia of the sub-chain move to the parent frame
+                    T fp[6];
+                    force_to_parent(m, i, jv[i], f[i], fp);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) f[i - 1][k] += fp[k];
+                    // variable stage: rotate by Rz(q)
+                    const T c = jv[i].c, s = jv[i].s;
+                    const T c2 = c * c - s * s, s2 = 2.0 * (c * s);
+                    rotz_sym(cI, c, s, c2, s2);
+                    const T mx = c * cmc[0] - s * cmc[1], my = s * cmc[0] + c * cmc[1];
+                    cmc[0] = mx; cmc[1] = my;
+                    // constant stage: rotate by Rp, shift by pp:  Io' = R Io R^T + (2 a.p + m p.p) 1 - (a p^T + p a^T + m p p^T)
+                    T RI[6], a3[3];
+                    rot_sym(m, i, cI, RI);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) a3[r] = m.Rp(i, 3 * r) * cmc[0] + m.Rp(i, 3 * r + 1) * cmc[1] + m.Rp(i, 3 * r + 2) * cmc[2];
+                    const double p0 = m.pp(i, 0), p1 = m.pp(i, 1), p2 = m.pp(i, 2);
+                    const T ap = a3[0] * p0 + a3[1] * p1 + a3[2] * p2;
+                    const T dg = 2.0 * ap + cm * (p0 * p0 + p1 * p1 + p2 * p2);
+                    const double pv[3] = {p0, p1, p2};
+                    const int rr[6] = {0, 0, 0, 1, 1, 2}, cc[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        T e = RI[k] - (a3[rr[k]] * pv[cc[k]] + a3[cc[k]] * pv[rr[k]] + cm * (pv[rr[k]] * pv[cc[k]]));
+                        if (rr[k] == cc[k]) e += dg;
+                        cI[k] = e;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) cmc[r] = a3[r] + cm * pv[r];
+                }
+            }
+        }
+        // per chain: M = Lm D Lm^T, then solve for qdd
+        bool ok = true;
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += L) {
+            T Lm[L][L], LD[L][L], Dinv[L], x[L];
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                T d = Mx[c0 + j][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
+                if (value_of(d) == 0.0) { ok = false; d = T(1.0); }
+                Dinv[j] = recip(d);
+#pragma unroll
+                for (int i = j + 1; i < L; ++i) {
+                    T e = Mx[c0 + i][j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) e -= Lm[i][k] * LD[j][k];
+                    LD[i][j] = e;
+                    Lm[i][j] = e * Dinv[j];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < L; ++i) {
+                x[i] = tau[c0 + i] - h[c0 + i];
+#pragma unroll
+                for (int k = 0; k < i; ++k) x[i] -= Lm[i][k] * x[k];
+            }
+#pragma unroll
+            for (int i = 0; i < L; ++i) x[i] = x[i] * Dinv[i];
+#pragma unroll
+            for (int i = L - 1; i >= 0; --i) {
+#pragma unroll
+                for (int k = i + 1; k < L; ++k) x[i] -= Lm[k][i] * x[k];
+                qdd[c0 + i] = x[i];
+            }
+        }
+        return ok;
+    }
+
+    // forward dynamics: through M for short static chains, ABA otherwise
+    static MPCF_DI bool fd(const MP &m, const T *q, const T *qd, const T *tau, T *qdd)
+    {
+        if constexpr (MP::kStatic && MP::kChain > 0 && MP::kChain <= 8) return fd_crba<MP::kChain>(m, q, qd, tau, qdd);
+        else return aba(m, q, qd, tau, qdd);
+    }
+
     // xdot = (qd, FD(q, qd, tau), fatigue_rhs); x = [q | qd | f]
     static MPCF_DI bool xdot(const MP &m, const T *x, const T *tau, T *k)
     {
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
-        bool ok = aba(m, x, x + n, tau, k + n);
+        bool ok = fd(m, x, x + n, tau, k + n);
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) {
             k[i] = x[n + i];

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) k_fd_derivs(const __grid_constant__ 
     double a[N], b[N], c[N], qdd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = tau[i * U + u]; }
-    Dyn<double, StaticModel<N, L>>::aba(m, a, b, c, qdd);
+    Dyn<double, StaticModel<N, L>>::fd(m, a, b, c, qdd);
     double A[N * N], B[N * N], C[N * N];
     FdDerivs<StaticModel<N, L>, L>::run(m, a, b, qdd, A, B, C);
 #pragma unroll

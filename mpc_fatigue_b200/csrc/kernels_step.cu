@@ -16,7 +16,7 @@ struct AbaBody {
             b[i] = qd[i * U + u];
             c[i] = tau[i * U + u];
         }
-        Dyn<double, MP>::aba(m, a, b, c, t);
+        Dyn<double, MP>::fd(m, a, b, c, t);
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) qdd[i * U + u] = t[i];
     }

@@ -24,6 +24,7 @@ template <int N, int L>
 struct StaticModel {
     static constexpr int MAXN = N;
     static constexpr bool kStatic = true;
+    static constexpr int kChain = L;  // length of each serial chain of the forest
     const StaticParams<N> &P;
     MPCF_DI int n() const { return N; }
     MPCF_DI int parent(int i) const { return (i % L == 0) ? -1 : i - 1; }
@@ -42,6 +43,7 @@ template <int MAXN_>
 struct GenericModel {
     static constexpr int MAXN = MAXN_;
     static constexpr bool kStatic = false;
+    static constexpr int kChain = 0;
     int n_;
     const double *d;  // shared memory
     const int *ii;    // shared memory
