@@ -151,3 +151,81 @@ def test_step_rk4_jvp(setup, direct):
     assert np.all(gj[: 2 * n, 3 * n : 4 * n] == 0.0)
     off = gj[2 * n :, 3 * n : 4 * n] * (1 - np.eye(n))[:, :, None]
     assert np.all(off == 0.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the batch axis and of the workspace pipeline
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("U", [1, 31, 33, 96])
+def test_ragged_batches_through_the_workspace_pipeline(U):
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import Model, data_urdf
+    from oracle.pyoracle import Oracle
+    from oracle.urdf_model import load_urdf
+    xml = data_urdf("pilz6")
+    m, om = Model.from_urdf(xml, armature=1e-2), load_urdf(xml, armature=1e-2)
+    ev, orc = BatchEvaluator(m), Oracle(om)
+    q, qd, tau, f, _ = random_inputs(om, U, seed=U)
+    dtu = np.ascontiguousarray(np.random.default_rng(U).uniform(0.002, 0.03, U))
+    rq, rqd, rf, rj = orc.step_rk4_jvp(q, qd, tau, f, 0.0, dt_u=dtu)
+    d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f)]
+    gq, gqd, gf, gj = ev.step_rk4_jvp(*d, torch.from_numpy(dtu).cuda())  # per-unit dt through K1/K3
+    assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
+    assert rel_err(gj.cpu().numpy(), rj) < TOL
+
+
+def test_workspace_smaller_than_batch_is_chunked():
+    """A caller-provided workspace for 64 units must serve U = 257 in five chunks with identical results."""
+    import ctypes as C
+    import torch
+    from mpc_fatigue_b200 import _capi
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import Model, data_urdf
+    from mpc_fatigue_b200.synth import synth_batch
+    m = Model.from_urdf(data_urdf("pilz6"), armature=1e-2)
+    ev = BatchEvaluator(m)
+    lim = {k: m.export(k) for k in ("q_lo", "q_hi", "v_max", "tau_max")}
+    U = 257
+    q, qd, tau, f = synth_batch(lim, 0, U, 1, device="cuda")
+    ref = ev.step_rk4_jvp(q, qd, tau, f, 0.02)
+    need64 = int(_capi.lib.mpcf_step_rk4_jvp_workspace_bytes(m.handle, 64))
+    assert need64 == 64 * 528 * 8 and int(_capi.lib.mpcf_step_rk4_jvp_workspace_bytes(m.handle, 1 << 24)) == (1 << 20) * 528 * 8
+    ws = torch.empty(need64 // 8, dtype=torch.float64, device="cuda")
+    out = [torch.empty_like(q) for _ in range(3)]
+    jac = torch.empty((18, 25, U), dtype=torch.float64, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    launches0 = _capi.lib.mpcf_launch_count()
+    rc = _capi.lib.mpcf_step_rk4_jvp_ws_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]),
+                                              p(jac), p(ws), need64, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc)
+    assert _capi.lib.mpcf_launch_count() - launches0 == 3 * 5
+    torch.cuda.synchronize()
+    assert torch.equal(jac, ref[3]) and all(torch.equal(a, b) for a, b in zip(out, ref[:3]))
+    # a workspace below one 32-unit tile falls back to the direct kernel (results agree to rounding)
+    rc = _capi.lib.mpcf_step_rk4_jvp_ws_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]),
+                                              p(jac), p(ws), 1024, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _capi.check(rc)
+    assert float((jac - ref[3]).abs().max() / ref[3].abs().max()) < 1e-11
+
+
+def test_max_dof_chain():
+    """MPCF_MAX_DOF = 64 joints through the run-time-topology kernels (per-link state in local memory)."""
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import Model
+    from oracle.pyoracle import Oracle
+    m = Model.synthetic("chain", 64, seed=5, armature=1e-3)
+    assert m.kernel_family == "generic64"
+    om = oracle_model_from_export(m)
+    ev, orc = BatchEvaluator(m), Oracle(om)
+    U = 40
+    q, qd, tau, f, qdd = random_inputs(om, U, seed=1)
+    qd *= 0.1  # 64 stacked joints: keep the tip velocity moderate
+    d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f, qdd)]
+    assert rel_err_rows(ev.rnea(d[0], d[1], d[4]).cpu().numpy(), orc.rnea(q, qd, qdd)) < TOL
+    assert rel_err_rows(ev.aba(d[0], d[1], d[2]).cpu().numpy(), orc.aba(q, qd, tau)) < 1e-8
+    r = orc.step_rk4(q, qd, tau, f, 0.001)
+    g = ev.step_rk4(d[0], d[1], d[2], d[3], 0.001)
+    for a, b in zip(g, r):
+        assert rel_err_rows(a.cpu().numpy(), b) < 1e-8
