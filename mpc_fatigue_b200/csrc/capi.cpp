@@ -16,6 +16,7 @@ struct mpcf_model {
     Family fam = FAM_GENERIC64;
     // static-family parameter block (largest variant), filled for the family in use
     StaticParams<12> sp12;
+    StaticParams<6> chain6[2];  // forest12x6: the two arms as stand-alone 6-DOF chains
     StaticParams<6> sp6;
     StaticParams<3> sp3;
     // device copy of the generic blob, uploaded lazily on first launch (model creation needs no GPU)
@@ -78,7 +79,24 @@ static void refresh(mpcf_model *m)
     const HostModel &h = m->h;
     if (h.n == 3 && is_forest(h, 3)) { m->fam = FAM_CHAIN3; fill_static(h, m->sp3); }
     else if (h.n == 6 && is_forest(h, 6)) { m->fam = FAM_CHAIN6; fill_static(h, m->sp6); }
-    else if (h.n == 12 && is_forest(h, 6)) { m->fam = FAM_FOREST12x6; fill_static(h, m->sp12); }
+    else if (h.n == 12 && is_forest(h, 6)) {
+        m->fam = FAM_FOREST12x6;
+        fill_static(h, m->sp12);
+        for (int c = 0; c < 2; ++c) {
+            StaticParams<6> &p = m->chain6[c];
+            for (int i = 0; i < 6; ++i) {
+                const int g = 6 * c + i;
+                std::memcpy(p.Rp[i], m->sp12.Rp[g], sizeof p.Rp[i]);
+                std::memcpy(p.pp[i], m->sp12.pp[g], sizeof p.pp[i]);
+                p.mass[i] = m->sp12.mass[g];
+                std::memcpy(p.mc[i], m->sp12.mc[g], sizeof p.mc[i]);
+                std::memcpy(p.Io[i], m->sp12.Io[g], sizeof p.Io[i]);
+                p.arm[i] = m->sp12.arm[g];
+                std::memcpy(p.fat[i], m->sp12.fat[g], sizeof p.fat[i]);
+            }
+            std::memcpy(p.grav, m->sp12.grav, sizeof p.grav);
+        }
+    }
     else m->fam = h.n <= 16 ? FAM_GENERIC16 : FAM_GENERIC64;
     m->dirty = true;
     m->fd_status = 0;
@@ -235,11 +253,12 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
     lm.fam = m->fam;
     lm.n = h.n;
     lm.static_params = nullptr;
+    lm.chain_params = nullptr;
     lm.blob = GenericBlob{nullptr, nullptr, h.n};
     switch (m->fam) {
     case FAM_CHAIN3: lm.static_params = &m->sp3; return MPCF_OK;
     case FAM_CHAIN6: lm.static_params = &m->sp6; return MPCF_OK;
-    case FAM_FOREST12x6: lm.static_params = &m->sp12; return MPCF_OK;
+    case FAM_FOREST12x6: lm.static_params = &m->sp12; lm.chain_params = m->chain6; return MPCF_OK;
     default: break;
     }
     std::lock_guard<std::mutex> lk(m->mu);
@@ -418,7 +437,8 @@ extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, lon
     if (!jvp2_supported(lm)) return 0;
     long units = U < kJvpChunkUnits ? U : kJvpChunkUnits;
     units = (units + 31) / 32 * 32;
-    return (size_t)units * jvp_ws_doubles_per_unit(model->h.n) * sizeof(double);
+    const int nchain = model->fam == FAM_FOREST12x6 ? 6 : model->h.n;  // forests run one chain at a time
+    return (size_t)units * jvp_ws_doubles_per_unit(nchain) * sizeof(double);
 }
 
 extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
@@ -428,7 +448,7 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
     PROLOGUE(q && qd && tau && f && jac)
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
-    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(model->h.n) * sizeof(double);
+    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(model->fam == FAM_FOREST12x6 ? 6 : model->h.n) * sizeof(double);
     if (!jvp2_supported(lm) || !workspace || workspace_bytes < min_ws)  // no workspace path: direct dual-number kernel
         return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
     if (reinterpret_cast<uintptr_t>(workspace) % 8) return fail(MPCF_EINVAL, "workspace must be 8-byte aligned");

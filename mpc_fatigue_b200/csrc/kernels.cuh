@@ -46,6 +46,7 @@ struct LaunchModel {
     int n;
     GenericBlob blob;
     const void *static_params;  // host pointer to StaticParams<N> for static families
+    const void *chain_params;   // forests: host array of StaticParams<L>, one per chain
 };
 
 struct CostArgs {

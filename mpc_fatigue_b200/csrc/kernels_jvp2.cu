@@ -260,23 +260,39 @@ struct ColumnState {
         a.finish(P, s, w + 3 * N * N * 32, h, na);
         b.finish(P, s, w + 3 * N * N * 32, h, nb);
     }
-    MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac) const
+    // Write this column into the Jacobian of the WHOLE model (ntot joints; this chain owns joints c0 .. c0+N-1): own rows
+    // get the values, the rows of the other chains are structurally zero.  The dt column is shared by all chains, so
+    // there only the own rows are written (every chain's launch writes its part).
+    // WHOLE: the chain is the whole model (ntot = N, c0 = 0) and every offset is a compile-time constant
+    template <bool WHOLE>
+    MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac, int ntot_, int c0_) const
     {
-        constexpr long PC = 4 * N + 1;
-        const long ocol = isdt ? 4 * N : col;
+        const int ntot = WHOLE ? N : ntot_, c0 = WHOLE ? 0 : c0_;
+        const long PC = 4 * ntot + 1;
+        const long ocol = isdt ? 4 * ntot : (col / N) * ntot + c0 + col % N;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            __stcs(jac + ((size_t)i * PC + ocol) * U + u, aq[i]);
-            __stcs(jac + ((size_t)(N + i) * PC + ocol) * U + u, av[i]);
-            __stcs(jac + ((size_t)(2 * N + i) * PC + ocol) * U + u, af[i]);
+            __stcs(jac + ((size_t)(c0 + i) * PC + ocol) * U + u, aq[i]);
+            __stcs(jac + ((size_t)(ntot + c0 + i) * PC + ocol) * U + u, av[i]);
+            __stcs(jac + ((size_t)(2 * ntot + c0 + i) * PC + ocol) * U + u, af[i]);
         }
-        if (isdt) {  // the n fatigue columns in closed form (see kernels_jvp.cu)
+        if (!WHOLE && !isdt) {
+            for (int blk = 0; blk < 3; ++blk)
+                for (int i = 0; i < ntot; ++i)
+                    if (i < c0 || i >= c0 + N) __stcs(jac + ((size_t)(blk * ntot + i) * PC + ocol) * U + u, 0.0);
+        }
+        if (isdt) {  // the fatigue columns of this chain in closed form (see kernels_jvp.cu), all 3*ntot rows
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double z = P.fat[j][0] * h;
                 const double g = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
+                if (WHOLE) {
 #pragma unroll
-                for (int r = 0; r < 3 * N; ++r) __stcs(jac + ((size_t)r * PC + 3 * N + j) * U + u, (r == 2 * N + j) ? g : 0.0);
+                    for (int r = 0; r < 3 * N; ++r) __stcs(jac + ((size_t)r * PC + 3 * N + j) * U + u, (r == 2 * N + j) ? g : 0.0);
+                } else {
+                    for (int r = 0; r < 3 * ntot; ++r)
+                        __stcs(jac + ((size_t)r * PC + 3 * ntot + c0 + j) * U + u, (r == 2 * ntot + c0 + j) ? g : 0.0);
+                }
             }
         }
     }
@@ -329,10 +345,10 @@ MPCF_DI void tma_issue(unsigned item, double *buf, unsigned long long *full, uns
 // Persistent chain-rule kernel for N <= 6.  CPW = Jacobian columns per consumer thread (1 or 2); NW consumer warps.
 // No dedicated producer warp: lane 0 of warp 0 refills the ring slot that was released NBUF-1 stages ago before it
 // starts its own stage (the slot is free by then unless the whole CTA is memory-starved).
-template <int N, int L, int NBUF, int CPW>
+template <int N, int L, int NBUF, int CPW, bool WHOLE>
 __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
     k_chain_rule_tma(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
-                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac)
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, int ntot, int c0)
 {
     using W = WsLayout<N>;
     constexpr int NC = 3 * N + 1;
@@ -380,8 +396,8 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
             if (lane == 0) mbar_arrive(&empty[slot]);
         }
         if (live) {
-            a.store(P, col0, h, U, u, jac);
-            if (two) b.store(P, col1, h, U, u, jac);
+            a.template store<WHOLE>(P, col0, h, U, u, jac, ntot, c0);
+            if (two) b.template store<WHOLE>(P, col1, h, U, u, jac, ntot, c0);
         }
     }
 }
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
 template <int N, int L, int NCY>
 __global__ void __launch_bounds__(32 * NCY, 2)
     k_chain_rule_ldg(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
-                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac)
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, int ntot, int c0)
 {
     using W = WsLayout<N>;
     const long lu = (long)blockIdx.x * 32 + threadIdx.x;
@@ -405,7 +421,7 @@ __global__ void __launch_bounds__(32 * NCY, 2)
         st.tauj = st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0;
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) st.stage(P, s, ws + W::chunk(blockIdx.x, s) + threadIdx.x, h);
-        st.store(P, col, h, U, u, jac);
+        st.template store<false>(P, col, h, U, u, jac, ntot, c0);
     }
 }
 
@@ -461,7 +477,7 @@ static int sm_count()
 template <int N, int L>
 static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, const double *qd, const double *tau, const double *f,
                             double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws, long Uc,
-                            cudaStream_t s)
+                            cudaStream_t s, int ntot = N, int c0 = 0)
 {
     using W = WsLayout<N>;
     constexpr int NBUF = (N <= 6) ? ((6 * W::kStageBytes + 256 <= 227 * 1024) ? 6 : 4) : 0;
@@ -469,9 +485,11 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
     if constexpr (N <= 6) {
         static bool attr_set = false;
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             attr_set = true;
         }
@@ -498,10 +516,11 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         if constexpr (N <= 6) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
             static const int cpw = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
-            if (cpw == 2) k_chain_rule_tma<N, L, NBUF, 2><<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
-            else k_chain_rule_tma<N, L, NBUF, 1><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+            if (cpw == 2) k_chain_rule_tma<N, L, NBUF, 2, true><<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            else if (ntot == N) k_chain_rule_tma<N, L, NBUF, 1, true><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            else k_chain_rule_tma<N, L, NBUF, 1, false><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
         } else {
-            k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac);
+            k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
         }
         prof_end(s);
         g_launches.fetch_add(3);
@@ -516,7 +535,7 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
                                size_t ws_bytes, cudaStream_t s)
 {
     if (U <= 0) return cudaSuccess;
-    const size_t per_unit = jvp_ws_doubles_per_unit(m.n) * sizeof(double);
+    const size_t per_unit = jvp_ws_doubles_per_unit(m.fam == FAM_FOREST12x6 ? 6 : m.n) * sizeof(double);
     long Uc = (long)(ws_bytes / per_unit);
     Uc -= Uc % 32;  // whole 32-unit tiles
     if (Uc < 32) return cudaErrorInvalidValue;
@@ -526,7 +545,19 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
     case FAM_CHAIN6:
         return run_jvp2<6, 6>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
     case FAM_FOREST12x6:
-        return run_jvp2<12, 6>(*static_cast<const StaticParams<12> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+    {   // the chains are dynamically decoupled: one 6-DOF pipeline per chain on its own input planes, writing its block
+        // of the 36 x 49 Jacobian (and the zeros of the cross blocks)
+        const StaticParams<6> *cp = static_cast<const StaticParams<6> *>(m.chain_params);
+        Uc = (long)(ws_bytes / (jvp_ws_doubles_per_unit(6) * sizeof(double)));
+        Uc -= Uc % 32;
+        for (int c = 0; c < 2; ++c) {
+            const size_t off = (size_t)c * 6 * U;
+            cudaError_t e = run_jvp2<6, 6>(cp[c], U, q + off, qd + off, tau + off, f + off, dt, dt_u, qn ? qn + off : nullptr,
+                                           qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, ws, Uc, s, 12, 6 * c);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     default:
         return cudaErrorInvalidValue;
     }
