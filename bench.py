@@ -294,7 +294,7 @@ def run_gpu(args) -> None:
     # ---- end to end through the host-facing API: pinned host inputs -> H2D -> kernels -> D2H of states + Jacobian ----
     del jac
     torch.cuda.empty_cache()
-    pipe = HostStepPipeline(model, dev, chunk_units=1 << 19)
+    pipe = HostStepPipeline(model, dev, chunk_units=1 << 19, skip_structural_zeros=True)
     hq, hqd, htau, hf = (torch.empty((n, U), dtype=torch.float64).pin_memory() for _ in range(4))
     for h_, d_ in ((hq, q), (hqd, qd), (htau, tau), (hf, f)):
         h_.copy_(d_)
@@ -330,8 +330,8 @@ def run_gpu(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]),
                     "d2h_bytes_per_step": int(stats["d2h_bytes"]), "steps": e2e_steps,
                     "what": "HostStepPipeline.run: pinned host q,qd,tau,f -> chunked H2D -> step_rk4_jvp + cost_residual -> "
-                            "D2H of q+,qd+,f+, dense Jacobian and per-scenario cost/residuals into pinned host staging "
-                            "(PCIe-bound: 3.9 KB of Jacobian per unit)"},
+                            "D2H of q+,qd+,f+, the 348 structurally non-zero Jacobian planes (of 450: d(q+,qd+)/df = 0, df+/df "
+                            "diagonal) and per-scenario cost/residuals into pinned host staging (PCIe-bound: 2.9 KB per unit)"},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": best_tf, "unit": "TFLOP/s", "frac": ach_tf / best_tf,
                          "traffic": TRAFFIC_BYTES_PER_UNIT * U if TRAFFIC_BYTES_PER_UNIT else None,
                          "traffic_source": "profiles/r01_jvp_pipeline.md: dram read+write of the 3 kernels per unit x U (ncu --set full)",

@@ -20,7 +20,7 @@ from .model import Model
 
 
 class HostStepPipeline:
-    def __init__(self, model: Model, device, chunk_units: int = 1 << 19, with_jacobian: bool = True):
+    def __init__(self, model: Model, device, chunk_units: int = 1 << 19, with_jacobian: bool = True, skip_structural_zeros: bool = False):
         self.model, self.dev = model, torch.device(device)
         self.ev = BatchEvaluator(model, self.dev)
         self.chunk_units = int(chunk_units)
@@ -28,6 +28,28 @@ class HostStepPipeline:
         self.n = model.n
         self._shape = None
         self.reduced = None
+        # Device output planes per unit: q+ (n), qd+ (n), f+ (n), then the Jacobian planes r*(4n+1)+c.  With
+        # skip_structural_zeros only the planes that can be non-zero travel to the host: d(q+, qd+)/df = 0 and df+/df is
+        # diagonal, i.e. 348 of 450 Jacobian planes for n = 6.  `plane_map[k]` = device plane of host row k.
+        n = self.n
+        P = 4 * n + 1
+        planes = list(range(3 * n))
+        if with_jacobian:
+            for r in range(3 * n):
+                for c in range(P):
+                    fcol = 3 * n <= c < 4 * n
+                    if skip_structural_zeros and fcol and not (r >= 2 * n and c - 3 * n == r - 2 * n):
+                        continue
+                    planes.append(3 * n + r * P + c)
+        self.plane_map = planes
+        self.segments = []  # (device plane start, host row start, count) of contiguous runs
+        k = 0
+        while k < len(planes):
+            j = k
+            while j + 1 < len(planes) and planes[j + 1] == planes[j] + 1:
+                j += 1
+            self.segments.append((planes[k], k, j - k + 1))
+            k = j + 1
 
     def _alloc(self, B: int, N: int):
         n = self.n
@@ -40,7 +62,7 @@ class HostStepPipeline:
         self.d_in = [torch.empty((4 * n, Uc), **f64) for _ in range(2)]
         self.d_out = [torch.empty((out_rows, Uc), **f64) for _ in range(2)]
         self.d_red = [torch.empty((4, Bc), **f64) for _ in range(2)]
-        self.h_out = [torch.empty((out_rows, Uc), dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.h_out = [torch.empty((len(self.plane_map), Uc), dtype=torch.float64).pin_memory() for _ in range(2)]
         self.h_red = torch.empty((4, B), dtype=torch.float64).pin_memory()
         self.reduced = torch.empty((4, B), **f64)
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
@@ -48,8 +70,8 @@ class HostStepPipeline:
 
     def run(self, hq, hqd, htau, hf, dt: float, B: int, N: int, consume=None) -> dict:
         """hq.. : pinned host float64 tensors [n, N*B] (node-major units).  `consume(view, b0, b1)` is called for
-        every finished chunk with the pinned staging view [rows, N, b1-b0] (rows = q+, qd+, f+, then the
-        Jacobian planes r*(4n+1)+c); without it the staging buffers are simply overwritten chunk after chunk."""
+        every finished chunk with the pinned staging view [rows, N, b1-b0] (host row k = device plane `plane_map[k]`:
+        q+, qd+, f+, then the Jacobian planes r*(4n+1)+c); without it the staging buffers are simply overwritten."""
         n = self.n
         for t in (hq, hqd, htau, hf):
             if not (t.dtype == torch.float64 and t.is_pinned() and t.is_contiguous() and tuple(t.shape) == (n, N * B)):
@@ -61,6 +83,7 @@ class HostStepPipeline:
         ev_out = [None, None]
         pending = []
         rows = self.d_out[0].shape[0]
+        hrows = len(self.plane_map)
         cur = torch.cuda.current_stream(self.dev)
         start = torch.cuda.Event()
         start.record(cur)
@@ -70,7 +93,7 @@ class HostStepPipeline:
         def hand_over(item):
             sl, a0, a1, e = item
             e.synchronize()
-            consume(self.h_out[sl].reshape(-1)[:rows * (a1 - a0) * N].view(rows, N, a1 - a0), a0, a1)
+            consume(self.h_out[sl].reshape(-1)[:hrows * (a1 - a0) * N].view(hrows, N, a1 - a0), a0, a1)
 
         with torch.cuda.device(self.dev):
             for ci, b0 in enumerate(range(0, B, Bc)):
@@ -113,8 +136,10 @@ class HostStepPipeline:
                 if consume is not None and len(pending) == 2:  # the slot about to be overwritten goes to the consumer first
                     hand_over(pending.pop(0))
                 with torch.cuda.stream(self.s_out):
-                    self.h_out[slot].reshape(-1)[:rows * uc].copy_(d_out.reshape(-1)[:rows * uc], non_blocking=True)
-                d2h += rows * uc * 8
+                    hflat, dflat = self.h_out[slot].reshape(-1), d_out.reshape(-1)
+                    for dp, hr, cnt in self.segments:  # one DMA per contiguous run of planes
+                        hflat[hr * uc:(hr + cnt) * uc].copy_(dflat[dp * uc:(dp + cnt) * uc], non_blocking=True)
+                d2h += hrows * uc * 8
                 ev_out[slot] = torch.cuda.Event()
                 ev_out[slot].record(self.s_out)
                 if consume is not None:

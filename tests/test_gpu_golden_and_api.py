@@ -142,6 +142,17 @@ def test_host_pipeline_matches_direct_calls(torch_mod):
     for (b0, b1), v in got.items():
         assert torch.equal(v, full[:, :, b0:b1])
     assert torch.equal(pipe.h_red, red.cpu())
+    # structural zeros stay on the device: 348 of 450 Jacobian planes travel, mapped by plane_map
+    pz = HostStepPipeline(m, "cuda:0", chunk_units=N * 256, skip_structural_zeros=True)
+    assert len(pz.plane_map) == 18 + 348 and len(pz.segments) < 30
+    gz = {}
+    st2 = pz.run(*host, dt, B, N, consume=lambda v, b0, b1: gz.__setitem__((b0, b1), v.clone()))
+    assert st2["d2h_bytes"] == (18 + 348) * B * N * 8 + 4 * B * 8
+    sel = torch.tensor(pz.plane_map)
+    for (b0, b1), v in gz.items():
+        assert torch.equal(v, full[sel][:, :, b0:b1])
+    dropped = sorted(set(range(468)) - set(pz.plane_map))
+    assert len(dropped) == 102 and float(full[torch.tensor(dropped)].abs().max()) == 0.0
 
 
 def test_full_size_properties(torch_mod):
