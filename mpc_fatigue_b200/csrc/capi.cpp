@@ -24,6 +24,7 @@ struct mpcf_model {
     mutable double *d_dbl = nullptr;
     mutable int *d_int = nullptr;
     mutable bool dirty = true;
+    mutable int device = -1;  // device holding the uploaded blob (run-time-topology families)
     int fd_status = 0;  // 0 unknown, 1 ok, -1 singular
 };
 
@@ -262,6 +263,10 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
     default: break;
     }
     std::lock_guard<std::mutex> lk(m->mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!m->dirty && m->device != dev)
+        return fail(MPCF_EINVAL, "model constants were uploaded to device " + std::to_string(m->device) + "; create one model handle per device");
     if (m->dirty) {
         const int n = h.n;
         std::vector<double> d;
@@ -278,6 +283,7 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
         if ((e = cudaMemcpy(m->d_dbl, d.data(), d.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(model)");
         if ((e = cudaMemcpy(m->d_int, ii.data(), ii.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy(model)");
         m->dirty = false;
+        m->device = dev;
     }
     lm.blob.dbl = m->d_dbl;
     lm.blob.ints = m->d_int;

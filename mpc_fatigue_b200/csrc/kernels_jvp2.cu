@@ -462,16 +462,21 @@ int jvp_profile_read(double *ms3, long *launches)
     return 0;
 }
 
+static int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < 64 ? dev : 0;
+}
 static int sm_count()
 {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+    static int n[64] = {};
+    const int dev = current_device();
+    if (!n[dev]) {
+        cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 template <int N, int L>
@@ -483,15 +488,18 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
     constexpr int NBUF = (N <= 6) ? ((6 * W::kStageBytes + 256 <= 227 * 1024) ? 6 : 4) : 0;
     constexpr size_t smem = (size_t)NBUF * W::kStageBytes + 2 * NBUF * sizeof(unsigned long long);
     if constexpr (N <= 6) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[64] = {};  // function attributes are per device: set them once on each device a process uses
+        const int dev = current_device();
+        if (!attr_set[dev]) {
             cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            attr_set = true;
+            e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * N * kThreads * (int)sizeof(double));
+            if (e != cudaSuccess) return e;
+            attr_set[dev] = true;
         }
     }
     for (long u0 = 0; u0 < U; u0 += Uc) {
@@ -505,8 +513,6 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
         if (k2smem && N <= 6) {  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
             constexpr int slab = 18 * N * kThreads * (int)sizeof(double);
-            static bool once = false;
-            if (!once) { cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, slab); once = true; }
             k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
         } else {
             k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
