@@ -133,6 +133,13 @@ int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q,
 int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
                          double *A, double *B, double *C, void *stream);
 
+/* Inverse-dynamics derivatives at (q, qd, qdd) — what an NLP solver needs for the reference-mode torque rows
+   tau = ID(q, qd, 0) -/+ J^T W (python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:134): dtau_dq = d ID/d q,
+   dtau_dqd = d ID/d qd, M = d ID/d qdd (joint-space inertia incl. armature), each [n*n][U], plane row*n + col.
+   qdd may be NULL (= 0). */
+int mpcf_rnea_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *qdd,
+                           double *dtau_dq, double *dtau_dqd, double *M, void *stream);
+
 /* Per-scenario reduction over the N nodes of each of B scenarios (unit index u = k*B + b):
      cost[b]      = sum_k  w_qd |qd_k|^2 + w_tau |tau_k|^2
      resid[0][b]  = max_k |x+_k - x_{k+1}|_inf          multiple-shooting defect (k < N-1)

@@ -470,6 +470,13 @@ extern "C" int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const doubl
     return done(launch_fd_derivs(lm, U, q, qd, tau, A, B, C, st), "fd_derivs_batch");
 }
 
+extern "C" int mpcf_rnea_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *qdd, double *dtau_dq,
+                                      double *dtau_dqd, double *M, void *stream)
+{
+    PROLOGUE(q && qd && dtau_dq && dtau_dqd && M)
+    return done(launch_rnea_derivs(lm, U, q, qd, qdd, dtau_dq, dtau_dqd, M, st), "rnea_derivs_batch");
+}
+
 extern "C" int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd, const double *f,
                                         const double *tau, const double *qn, const double *qdn, const double *fn, double dt,
                                         double w_qd, double w_tau, double tau0, double alpha, double tau_floor, double f_max,

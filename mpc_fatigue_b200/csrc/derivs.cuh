@@ -122,7 +122,9 @@ struct FdDerivs {
 
     // KS: where the per-link (S, xi, eta) live between the passes: thread-local arrays (LocalLinkStore) or a
     // shared-memory slab with a conflict-free [slot][thread] layout (SharedLinkStore).
-    template <class Emit, class KS>
+    // SOLVE = true : emit A = dqdd/dq (mat 0), B = dqdd/dqd (1), C = M^-1 (2)              [forward-dynamics derivatives]
+    // SOLVE = false: emit dID/dq (mat 0), dID/dqd (1), M (2) at the given (q, qd, qdd)       [inverse-dynamics derivatives]
+    template <class Emit, class KS, bool SOLVE = true>
     static MPCF_DI void run_emit_ks(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit, KS &ks)
     {
         RigidInertiaW Iw[N];
@@ -316,6 +318,18 @@ struct FdDerivs {
                 }
             }
             M[k][k] += m.arm(k);
+        }
+        if (!SOLVE) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int cI = 0; cI < N; ++cI) {
+                    if (r / L != cI / L) continue;
+                    emit(0, r, cI, Dq[r][cI]);
+                    emit(1, r, cI, Dv[r][cI]);
+                    emit(2, r, cI, M[r][cI]);
+                }
+            return;
         }
         // ------------------------------------------------------------------ per chain: LDL^T, C = M^-1, A = -C Dq, B = -C Dv
 #pragma unroll

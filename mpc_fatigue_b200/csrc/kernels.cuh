@@ -74,6 +74,8 @@ size_t jvp_ws_doubles_per_unit(int n);
 cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                                double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws,
                                size_t ws_bytes, cudaStream_t s);
+cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
+                               double *M, cudaStream_t s);
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
                              double *C, cudaStream_t s);
 void jvp_profile_enable(bool on);

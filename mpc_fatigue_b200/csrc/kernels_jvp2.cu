@@ -141,6 +141,52 @@ __global__ void __launch_bounds__(kThreads) k_fd_derivs(const __grid_constant__ 
     }
 }
 
+// inverse-dynamics derivatives for static families: dtau/dq, dtau/dqd, M at (q, qd, qdd); thread = unit
+template <int N, int L>
+__global__ void __launch_bounds__(kThreads) k_rnea_derivs(const __grid_constant__ StaticParams<N> P, long U, const double *q, const double *qd,
+                                                         const double *qdd, double *Dq, double *Dv, double *Mo)
+{
+    const StaticModel<N, L> m{P};
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double a[N], b[N], c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
+    // cross-chain entries are structurally zero
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int cc = 0; cc < N; ++cc)
+            if (r / L != cc / L) { Dq[(size_t)(r * N + cc) * U + u] = 0.0; Dv[(size_t)(r * N + cc) * U + u] = 0.0; Mo[(size_t)(r * N + cc) * U + u] = 0.0; }
+    LocalLinkStore<N> ks;
+    auto emit = [&](int mat, int r, int cc, double v) { (mat == 0 ? Dq : (mat == 1 ? Dv : Mo))[(size_t)(r * N + cc) * U + u] = v; };
+    FdDerivs<StaticModel<N, L>, L>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
+}
+
+// generic fallback: one dual-number RNEA sweep per seed direction (blockIdx.y in [0, 3n): q, qd, qdd seeds)
+struct RneaDerivsDualBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
+                            double *Mo)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        const int n = m.n();
+        const int d = blockIdx.y;
+        Dual a[MP::MAXN], b[MP::MAXN], c[MP::MAXN], t[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            a[i] = Dual(q[i * U + u], d == i ? 1.0 : 0.0);
+            b[i] = Dual(qd[i * U + u], d == n + i ? 1.0 : 0.0);
+            c[i] = Dual(qdd ? qdd[i * U + u] : 0.0, d == 2 * n + i ? 1.0 : 0.0);
+        }
+        Dyn<Dual, MP>::rnea(m, a, b, c, t);
+        double *out = d < n ? Dq : (d < 2 * n ? Dv : Mo);
+        const int col = d % n;
+#pragma unroll UNR
+        for (int r = 0; r < n; ++r) out[(size_t)(r * n + col) * U + u] = t[r].d;
+    }
+};
+
 // generic fallback for fd-derivs: one dual-number ABA sweep per seed direction (blockIdx.y in [0, 3n))
 struct FdDerivsDualBody {
     template <class MP>
@@ -567,6 +613,25 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
     default:
         return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
+                               double *M, cudaStream_t s)
+{
+    if (U <= 0) return cudaSuccess;
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    switch (m.fam) {
+    case FAM_CHAIN3:
+        k_rnea_derivs<3, 3><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        break;
+    case FAM_CHAIN6:
+        k_rnea_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        break;
+    default:
+        return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
+    }
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,

@@ -151,6 +151,17 @@ class BatchEvaluator:
                                                        C.c_void_p(B.data_ptr()), C.c_void_p(Cm.data_ptr()), _stream()))
         return A, B, Cm
 
+    def rnea_derivs(self, q, qd, qdd=None):
+        """d tau/d q, d tau/d qd, M = d tau/d qdd of tau = inverse_dynamics(q, qd, qdd) as [n*n, U] planes (row*n + col):
+        the Jacobian blocks of the reference-mode torque rows (force_optimization_pilz_6DOF.py:134)."""
+        U, n = self._U(q), self.n
+        Dq, Dv, M = (self._out(None, n * n, U, nm) for nm in ("dtau_dq", "dtau_dqd", "M"))
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_rnea_derivs_batch(self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                                                         self._in(qdd, n, U, "qdd", True), C.c_void_p(Dq.data_ptr()),
+                                                         C.c_void_p(Dv.data_ptr()), C.c_void_p(M.data_ptr()), _stream()))
+        return Dq, Dv, M
+
     def _workspace(self, U: int):
         """Device workspace of the analytic Jacobian pipeline (cached; bounded by the library's chunking)."""
         need = int(_capi.lib.mpcf_step_rk4_jvp_workspace_bytes(self.model.handle, U))

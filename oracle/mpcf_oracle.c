@@ -251,3 +251,28 @@ int mpcfo_fd_derivs_batch(const mpcfo_model *m, long U, const double *q, const d
     }
     return rc ? -3 : 0;
 }
+
+/* Inverse-dynamics derivatives at (q, qd, qdd) by complex-step through rnea_c: Dq = d tau/d q, Dv = d tau/d qd,
+ * M = d tau/d qdd; outputs [n*n][U], plane row*n + col. */
+int mpcfo_rnea_derivs_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
+                            double *Dq, double *Dv, double *M)
+{
+    CHECK_N(m);
+    const int n = m->n;
+    const double hstep = 1e-40;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double complex a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], t[MPCFO_MAXN];
+        for (int d = 0; d < 3 * n; ++d) {
+            for (int i = 0; i < n; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
+            if (d < n) a[d] += hstep * I;
+            else if (d < 2 * n) b[d - n] += hstep * I;
+            else c[d - 2 * n] += hstep * I;
+            rnea_c(m, a, b, c, t);
+            double *out = d < n ? Dq : (d < 2 * n ? Dv : M);
+            int col = d % n;
+            for (int r = 0; r < n; ++r) out[((long)r * n + col) * U + u] = cimag(t[r]) / hstep;
+        }
+    }
+    return 0;
+}

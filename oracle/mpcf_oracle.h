@@ -63,6 +63,12 @@ int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const
 int mpcfo_fatigue_rhs_batch(const mpcfo_model *m, long U, const double *f, const double *tau, const double *qd,
                             double *fdot);
 
+/* complex-step derivatives: forward dynamics (A = dqdd/dq, B = dqdd/dqd, C = M^-1) and inverse dynamics */
+int mpcfo_fd_derivs_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *tau,
+                          double *A, double *B, double *Cm);
+int mpcfo_rnea_derivs_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
+                            double *Dq, double *Dv, double *M);
+
 #ifdef __cplusplus
 }
 #endif

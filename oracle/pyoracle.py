@@ -170,3 +170,12 @@ class Oracle:
         if rc != 0:
             raise ZeroDivisionError("ABA singular")
         return A, B, Cm
+
+    def rnea_derivs(self, q, qd, qdd=None):
+        """d tau/d q, d tau/d qd, M = d tau/d qdd as [n*n, U] planes (row*n + col)."""
+        n, U = q.shape
+        Dq, Dv, M = np.empty((n * n, U)), np.empty((n * n, U)), np.empty((n * n, U))
+        rc = self.lib.mpcfo_rnea_derivs_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                              _p(qdd if qdd is None else _chk(qdd, n, U)), _p(Dq), _p(Dv), _p(M))
+        assert rc == 0, rc
+        return Dq, Dv, M

@@ -128,6 +128,23 @@ def test_fd_derivs(setup):
     assert rel_err(gB.cpu().numpy(), rB) < TOL
 
 
+def test_rnea_derivs(setup):
+    q, qd, tau, f, qdd = setup["host"]
+    dq, dqd, dtau, df, dqdd = setup["dev"]
+    U = min(setup["U"], 40)
+    sl = lambda a: np.ascontiguousarray(a[:, :U])
+    dsl = lambda a: a[:, :U].contiguous()
+    for with_qdd in (True, False):
+        rDq, rDv, rM = setup["orc"].rnea_derivs(sl(q), sl(qd), sl(qdd) if with_qdd else None)
+        gDq, gDv, gM = setup["ev"].rnea_derivs(dsl(dq), dsl(dqd), dsl(dqdd) if with_qdd else None)
+        assert rel_err(gM.cpu().numpy(), rM) < TOL
+        assert rel_err(gDq.cpu().numpy(), rDq) < TOL
+        assert rel_err(gDv.cpu().numpy(), rDv) < TOL
+    # M is the joint-space inertia the oracle's CRBA computes
+    n = setup["m"].n
+    assert rel_err(gM.cpu().numpy()[:, 0].reshape(n, n), setup["orc"].crba(q[:, 0].copy())) < TOL
+
+
 @pytest.mark.parametrize("direct", [False, True], ids=["workspace", "direct"])
 def test_step_rk4_jvp(setup, direct):
     q, qd, tau, f, qdd = setup["host"]
