@@ -1,0 +1,128 @@
+"""casadi.Callback adapters: put the GPU evaluator inside a CasADi MX graph / an IPOPT solve.
+
+The reference builds its NLPs from SX-traced Functions and lets CasADi differentiate the graph
+(`nlpsol('solver', 'ipopt', nlp)`, python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:195-197).  A numeric GPU
+evaluator cannot be traced by SX; it enters an MX graph as a `casadi.Callback` that supplies its own Jacobian, and
+IPOPT runs with `hessian_approximation = limited-memory`.
+
+casadi is NOT installed in the build image, so this module is import-guarded and exercised only structurally
+(tests/test_host_and_boundary.py checks that it degrades with a clear error).  Layouts follow CasADi: every input
+and output is a dense column vector; batched quantities are stacked node-major, i.e. `q = vec([N, n])`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+try:  # pragma: no cover - casadi is absent in the build image
+    import casadi
+    HAVE_CASADI = True
+except ImportError:  # noqa: D401
+    casadi = None
+    HAVE_CASADI = False
+
+
+def require_casadi():
+    if not HAVE_CASADI:
+        raise ImportError("casadi is not installed: mpc_fatigue_b200.casadi_adapter needs it (pip install casadi); the "
+                          "look-alike in mpc_fatigue_b200.pynocchio_casadi works without it")
+
+
+def make_inverse_dynamics_callback(urdf: str, N: int, armature: float = 0.0, name: str = "gpu_inverse_dynamics"):
+    """Callback tau = ID(q, qdot, qddot) for all N nodes of a horizon in one GPU launch, with the block-diagonal
+    Jacobian [dtau/dq | dtau/dqdot | M] from mpcf_rnea_derivs_batch.  Inputs/outputs: vec([N, n])."""
+    require_casadi()
+    import torch
+
+    from .evaluator import BatchEvaluator
+    from .model import Model
+
+    model = Model.from_urdf(urdf, armature=armature)
+    ev = BatchEvaluator(model)
+    n = model.n
+
+    def to_dev(x):
+        return torch.from_numpy(np.ascontiguousarray(np.array(x, dtype=np.float64).reshape(N, n).T)).cuda()
+
+    class _Jac(casadi.Callback):
+        def __init__(self):
+            casadi.Callback.__init__(self)
+            self.construct(name + "_jac", {})
+
+        def get_n_in(self):
+            return 4  # q, qdot, qddot, (nominal output, unused)
+
+        def get_n_out(self):
+            return 3
+
+        def get_sparsity_in(self, i):
+            return casadi.Sparsity.dense(N * n, 1)
+
+        def get_sparsity_out(self, i):
+            return _block_diag_sparsity(N, n)
+
+        def eval(self, arg):
+            Dq, Dv, M = ev.rnea_derivs(to_dev(arg[0]), to_dev(arg[1]), to_dev(arg[2]))
+            return [_block_diag_dm(D.cpu().numpy(), N, n) for D in (Dq, Dv, M)]
+
+    class _ID(casadi.Callback):
+        def __init__(self):
+            casadi.Callback.__init__(self)
+            self._jac = _Jac()
+            self.construct(name, {})
+
+        def get_n_in(self):
+            return 3
+
+        def get_n_out(self):
+            return 1
+
+        def get_name_in(self, i):
+            return ("q", "qdot", "qddot")[i]  # the reference's input names, src/casadi_pinocchio_bridge.hpp:78
+
+        def get_name_out(self, i):
+            return "tau"
+
+        def get_sparsity_in(self, i):
+            return casadi.Sparsity.dense(N * n, 1)
+
+        def get_sparsity_out(self, i):
+            return casadi.Sparsity.dense(N * n, 1)
+
+        def eval(self, arg):
+            tau = ev.rnea(to_dev(arg[0]), to_dev(arg[1]), to_dev(arg[2]))
+            return [casadi.DM(tau.t().contiguous().cpu().numpy().reshape(-1))]
+
+        def has_jacobian(self):
+            return True
+
+        def get_jacobian(self, jname, inames, onames, opts):
+            return self._jac
+
+    return _ID()
+
+
+def _block_diag_sparsity(N: int, n: int):
+    rows, cols = [], []
+    for k in range(N):
+        for r in range(n):
+            for c in range(n):
+                rows.append(k * n + r)
+                cols.append(k * n + c)
+    return casadi.Sparsity.triplet(N * n, N * n, rows, cols)
+
+
+def _block_diag_dm(planes: np.ndarray, N: int, n: int):
+    """planes [n*n, N] (row*n + col) -> block-diagonal DM."""
+    out = casadi.DM(_block_diag_sparsity(N, n))
+    blocks = planes.T.reshape(N, n, n)
+    for k in range(N):
+        out[k * n:(k + 1) * n, k * n:(k + 1) * n] = blocks[k]
+    return out
+
+
+IPOPT_OPTIONS = {
+    # the evaluator supplies first derivatives only (reference default: exact Hessian from the SX graph;
+    # `limited-memory` appears in the reference only as a comment, python/Centauro_script/RepeatedMPCwithThermal.py:426)
+    "ipopt.hessian_approximation": "limited-memory",
+    "ipopt.print_level": 0,
+}

@@ -122,6 +122,15 @@ def test_function_lookalike_metadata_and_protocol():
             Idyn(q=[0.0] * 6, qdot=[0.0] * 6, qddot=[0.0] * 6)
 
 
+def test_casadi_adapter_degrades_cleanly_without_casadi():
+    from mpc_fatigue_b200 import casadi_adapter
+    if casadi_adapter.HAVE_CASADI:
+        pytest.skip("casadi is installed: the adapter is exercised by the integration, not by this guard test")
+    with pytest.raises(ImportError, match="casadi is not installed"):
+        casadi_adapter.make_inverse_dynamics_callback(data_urdf("pilz6"), N=4)
+    assert casadi_adapter.IPOPT_OPTIONS["ipopt.hessian_approximation"] == "limited-memory"
+
+
 def test_step_bound_table_and_solution_layout():
     lb, ub = step_bound_table(9, [(-np.ones(2) * 50, np.ones(2) * 50), (-np.ones(2) * 20, np.ones(2) * 20), (np.array([-5, -10.0]), np.array([5, 5.0]))])
     assert lb.shape == (9, 2) and ub[0, 0] == 50 and ub[3, 0] == 20 and lb[8].tolist() == [-5, -10]
