@@ -184,14 +184,25 @@ struct Dyn {
     // =========================================================================================
     static MPCF_DI void rnea(const MP &m, const T *q, const T *qd, const T *qdd, T *tau)
     {
+        JointVar<T> jv[MAXN];
+        rnea_impl<false>(m, q, jv, qd, qdd, tau);
+    }
+    // same with the joint variables (cos q, sin q / shift) already evaluated, so callers that also need frame
+    // kinematics share one sincos per joint
+    static MPCF_DI void rnea_jv(const MP &m, const JointVar<T> *jv, const T *qd, const T *qdd, T *tau)
+    {
+        rnea_impl<true>(m, nullptr, const_cast<JointVar<T> *>(jv), qd, qdd, tau);
+    }
+    template <bool HAVE_JV>
+    static MPCF_DI void rnea_impl(const MP &m, const T *q, JointVar<T> *jv, const T *qd, const T *qdd, T *tau)
+    {
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
-        JointVar<T> jv[MAXN];
         T v[MAXN][6], a[MAXN][6], f[MAXN][6];
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) {
+            if (!HAVE_JV) joint_var(m, i, q[i], jv[i]);  // interleaved with the link recursion: better ILP than hoisting all sincos
             const int par = m.parent(i), s = sidx(m, i);
-            joint_var(m, i, q[i], jv[i]);
             T vp[6], ap[6];
             if (par >= 0) {
 #pragma unroll
@@ -236,11 +247,19 @@ struct Dyn {
     {
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
+        JointVar<T> jv[MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) joint_var(m, i, q[i], jv[i]);
+        fk_all_jv(m, jv, oR, op);
+    }
+    static MPCF_DI void fk_all_jv(const MP &m, const JointVar<T> *jvs, T (*oR)[9], T (*op)[3])
+    {
+        const int n = m.n();
+        constexpr int UNR = MP::kStatic ? MAXN : 1;
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) {
             const int par = m.parent(i);
-            JointVar<T> jv;
-            joint_var(m, i, q[i], jv);
+            const JointVar<T> jv = jvs[i];
             // local liMi = (R, p)
             T R[9], p[3];
             if (!m.prismatic(i)) {

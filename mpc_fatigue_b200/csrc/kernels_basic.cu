@@ -103,10 +103,13 @@ struct NodeEvalBody {
             c[i] = (!jtw_only && qdd) ? qdd[i * U + u] : 0.0;
             t[i] = 0.0;
         }
-        if (!jtw_only) Dyn<double, MP>::rnea(m, a, b, c, t);
+        JointVar<double> jv[MP::MAXN];  // one sincos per joint, shared by the dynamics and the frame kinematics
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) Dyn<double, MP>::joint_var(m, i, a[i], jv[i]);
+        if (!jtw_only) Dyn<double, MP>::rnea_jv(m, jv, b, c, t);
         if (ee.nee > 0) {
             double oR[MP::MAXN][9], op[MP::MAXN][3];
-            Dyn<double, MP>::fk_all(m, a, oR, op);
+            Dyn<double, MP>::fk_all_jv(m, jv, oR, op);
             for (int e = 0; e < ee.nee; ++e) {
                 double pf[3], Rf[9], w[6];
                 Dyn<double, MP>::frame_pose(ee.f[e].joint, ee.f[e].R, ee.f[e].p, oR, op, pf, Rf);
