@@ -165,7 +165,8 @@ def run_reference(args) -> None:
     orc.step_rk4_jvp(q, qd, tau, f, DT)
     rate0 = U0 / (time.perf_counter() - t0)
     total = max(1, args.steps + args.warmup)
-    U = int(max(U0, min(2 ** 20, rate0 * 90.0 / total)))  # whole run ~ 90 s
+    budget_s = 2.0 if os.environ.get("MPCF_BENCH_QUICK") else 90.0  # whole run ~ 90 s (a few seconds in the contract test)
+    U = int(max(256, min(2 ** 20, rate0 * budget_s / total)))
     q, qd, tau, f = cpu_inputs(np, om, U)
     for _ in range(args.warmup):
         orc.step_rk4_jvp(q, qd, tau, f, DT)

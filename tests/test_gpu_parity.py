@@ -246,3 +246,28 @@ def test_max_dof_chain():
     g = ev.step_rk4(d[0], d[1], d[2], d[3], 0.001)
     for a, b in zip(g, r):
         assert rel_err_rows(a.cpu().numpy(), b) < 1e-8
+
+
+def test_zero_step_is_identity_with_k1_as_dt_column():
+    """dt = 0: x+ = x, d x+/d x = I, d x+/d tau = 0, d x+/d dt = xdot(x) — exercises the dt column of the chain rule."""
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import Model, data_urdf
+    from oracle.pyoracle import Oracle
+    from oracle.urdf_model import load_urdf
+    xml = data_urdf("pilz6")
+    m, om = Model.from_urdf(xml, armature=1e-2), load_urdf(xml, armature=1e-2)
+    ev, orc = BatchEvaluator(m), Oracle(om)
+    U = 37
+    q, qd, tau, f, _ = random_inputs(om, U, seed=8)
+    d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f)]
+    for direct in (False, True):
+        gq, gqd, gf, gj = ev.step_rk4_jvp(*d, 0.0, direct=direct)
+        assert torch.equal(gq, d[0]) and torch.equal(gqd, d[1]) and torch.equal(gf, d[3])
+        J = gj.cpu().numpy()
+        eye = np.zeros((18, 25))
+        eye[:12, :12] = np.eye(12)
+        eye[12:, 18:24] = np.eye(6)
+        assert np.abs(J[:, :24] - eye[:, :24, None]).max() < 1e-15
+        xdot = np.vstack([qd, orc.aba(q, qd, tau), orc.fatigue_rhs(f, tau, qd)])
+        assert rel_err_rows(J[:, 24], xdot) < TOL
