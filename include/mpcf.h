@@ -113,6 +113,12 @@ int mpcf_aba_batch(const mpcf_model *model, long U, const double *q, const doubl
 int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
                         const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
                         void *stream);
+/* Sequential rollout (single shooting) of B scenarios over N steps: x_{k+1} = RK4(x_k, tau_k, dt), x_0 = (q0, qd0, f0)
+   given as [n][B].  tau and the trajectory outputs qt/qdt/ft are [n][N*B] node-major (unit k*B + b); entry k of the
+   outputs is x_{k+1}.  One thread per scenario keeps the state in registers across the steps. */
+int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double *q0, const double *qd0,
+                           const double *f0, const double *tau, double dt, double *qt, double *qdt, double *ft,
+                           void *stream);
 /* Same plus the dense forward-mode Jacobian jac[3n][4n+1][U]:
    rows (q+, qd+, f+), columns (q, qd, tau, f, dt).  qn/qdn/fn may be NULL. */
 int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmpcf.so")
+LIB_PATH = os.environ.get("MPCF_LIB") or os.path.join(_HERE, "lib", "libmpcf.so")  # MPCF_LIB: A/B-test another build
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -50,6 +50,7 @@ _sig = {
                                            _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_aba_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_step_rk4_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, C.c_void_p]),
+    "mpcf_rollout_rk4_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_step_rk4_jvp_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp,
                                           C.c_void_p]),
     "mpcf_step_rk4_jvp_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_long]),

@@ -422,6 +422,16 @@ extern "C" int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double
     return done(launch_step(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, st), "step_rk4_batch");
 }
 
+extern "C" int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double *q0, const double *qd0, const double *f0,
+                                      const double *tau, double dt, double *qt, double *qdt, double *ft, void *stream)
+{
+    const long U = B;
+    PROLOGUE(q0 && qd0 && f0 && tau && qt && qdt && ft)
+    if (N <= 0) return fail(MPCF_EINVAL, "N must be positive");
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_rollout(lm, B, N, q0, qd0, f0, tau, dt, qt, qdt, ft, st), "rollout_rk4_batch");
+}
+
 extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
                                        const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
                                        double *jac, void *stream)

@@ -63,6 +63,8 @@ cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsig
 cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *qdd, cudaStream_t s);
 cudaError_t launch_step(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                         double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s);
+cudaError_t launch_rollout(const LaunchModel &m, long B, int N, const double *q0, const double *qd0, const double *f0, const double *tau,
+                           double dt, double *qt, double *qdt, double *ft, cudaStream_t s);
 cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                             double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s);
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,

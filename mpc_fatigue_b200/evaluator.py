@@ -141,6 +141,21 @@ class BatchEvaluator:
                 C.c_void_p(fn.data_ptr()), _stream()))
         return qn, qdn, fn
 
+    def rollout_rk4(self, q0, qd0, f0, tau, N: int, dt: float):
+        """Single-shooting rollout of B scenarios over N steps: x0 tensors are [n, B], tau is [n, N*B] node-major
+        (unit k*B + b); returns (q, qd, f) trajectories [n, N*B] with entry k = x_{k+1}."""
+        if q0.dim() != 2:
+            raise ValueError("expected [n, B] initial states")
+        n, B = self.n, q0.shape[1]
+        U = B * int(N)
+        qt, qdt, ft = (self._out(None, n, U, nm) for nm in ("qt", "qdt", "ft"))
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_rollout_rk4_batch(
+                self.model.handle, B, int(N), self._in(q0, n, B, "q0"), self._in(qd0, n, B, "qd0"), self._in(f0, n, B, "f0"),
+                self._in(tau, n, U, "tau"), float(dt), C.c_void_p(qt.data_ptr()), C.c_void_p(qdt.data_ptr()),
+                C.c_void_p(ft.data_ptr()), _stream()))
+        return qt, qdt, ft
+
     def fd_derivs(self, q, qd, tau):
         """A = d qdd/d q, B = d qdd/d qd, C = M^-1 as [n*n, U] planes (row*n + col)."""
         U, n = self._U(q), self.n

@@ -115,6 +115,29 @@ def test_step_rk4(setup):
     assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
 
 
+def test_rollout_rk4(setup):
+    """Single-shooting rollout == N chained oracle steps; and == chaining the GPU's own per-node step kernel bit for bit."""
+    torch = setup["torch"]
+    q, qd, tau, f, qdd = setup["host"]
+    m = setup["m"]
+    n, B, N, dt = m.n, 9, 5, 0.004
+    rng = np.random.default_rng(21)
+    q0, qd0, f0 = (np.ascontiguousarray(a[:, :B]) for a in (q, 0.3 * qd, f))
+    taus = np.ascontiguousarray(np.tile(tau[:, :B], (1, N)) * rng.uniform(0.5, 1.0, (n, N * B)))
+    d = [torch.from_numpy(a).cuda() for a in (q0, qd0, f0, taus)]
+    gq, gqd, gf = setup["ev"].rollout_rk4(d[0], d[1], d[2], d[3], N, dt)
+    x = (q0, qd0, f0)
+    xs = (d[0], d[1], d[2])
+    for k in range(N):
+        tk = np.ascontiguousarray(taus[:, k * B:(k + 1) * B])
+        x = setup["orc"].step_rk4(x[0], x[1], tk, x[2], dt)
+        xs = setup["ev"].step_rk4(xs[0], xs[1], d[3][:, k * B:(k + 1) * B].contiguous(), xs[2], dt)
+        for got, ref, own in zip((gq, gqd, gf), x, xs):
+            blk = got[:, k * B:(k + 1) * B]
+            assert rel_err_rows(blk.cpu().numpy(), ref) < 1e-8  # N steps of error growth
+            assert torch.equal(blk, own)
+
+
 def test_fd_derivs(setup):
     q, qd, tau, f, qdd = setup["host"]
     dq, dqd, dtau, df, dqdd = setup["dev"]
