@@ -105,6 +105,11 @@ int mpcf_node_eval_ref_batch(const mpcf_model *model, int nee, const int *ee_fra
                              const double *q, const double *qd, const double *qdd, const double *W,
                              const double *T, double h, double *tau, double *qnext, double *Tnext,
                              void *stream);
+/* First derivatives of the reference-mode torque rows tau = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e:
+   dtau_dq, dtau_dqd as [n*n][U] (plane row*n + col).  d tau / d W_e = wsign * J_e^T: use mpcf_frame_jac_batch. */
+int mpcf_node_eval_ref_jvp_batch(const mpcf_model *model, int nee, const int *ee_frames, double wsign, long U,
+                                 const double *q, const double *qd, const double *qdd, const double *W,
+                                 double *dtau_dq, double *dtau_dqd, void *stream);
 /* qdd[n][U] = forward dynamics(q, qd, tau) */
 int mpcf_aba_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
                    double *qdd, void *stream);

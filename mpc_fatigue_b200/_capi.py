@@ -48,6 +48,8 @@ _sig = {
     "mpcf_frame_jac_t_wrench_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_long, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_node_eval_ref_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_long, _dp, _dp, _dp,
                                            _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_void_p]),
+    "mpcf_node_eval_ref_jvp_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_long, _dp, _dp, _dp, _dp, _dp, _dp,
+                                               C.c_void_p]),
     "mpcf_aba_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_step_rk4_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_rollout_rk4_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, C.c_void_p]),

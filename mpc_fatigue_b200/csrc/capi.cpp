@@ -406,6 +406,20 @@ extern "C" int mpcf_node_eval_ref_batch(const mpcf_model *model, int nee, const 
     return done(launch_node_eval(lm, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, false, st), "node_eval_ref_batch");
 }
 
+extern "C" int mpcf_node_eval_ref_jvp_batch(const mpcf_model *model, int nee, const int *ee_frames, double wsign, long U, const double *q,
+                                            const double *qd, const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd,
+                                            void *stream)
+{
+    PROLOGUE(q && qd && dtau_dq && dtau_dqd)
+    if (nee < 0 || nee > MPCF_MAX_EE) return fail(MPCF_EINVAL, "nee out of range (0..MPCF_MAX_EE)");
+    if (nee > 0 && (!ee_frames || (U > 0 && !W))) return fail(MPCF_EINVAL, "end-effector frames / wrenches missing");
+    EeArgs ee;
+    ee.nee = nee;
+    for (int e = 0; e < nee; ++e)
+        if (int rc = frame_arg(model, ee_frames[e], ee.f[e])) return rc;
+    return done(launch_node_eval_jvp(lm, ee, wsign, U, q, qd, qdd, W, dtau_dq, dtau_dqd, st), "node_eval_ref_jvp_batch");
+}
+
 extern "C" int mpcf_aba_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau, double *qdd,
                               void *stream)
 {

@@ -145,6 +145,66 @@ struct NodeEvalBody {
     }
 };
 
+// First derivatives of the reference-mode joint torque tau = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e with respect to
+// q and qd: one dual-number sweep per seed (blockIdx.y in [0, 2n)).  d tau/d W_e = wsign * J_e^T comes from the frame
+// Jacobian kernel.  These are the Jacobian blocks of the torque-bound rows of the reference's OCPs
+// (python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:134-148).
+struct NodeEvalJvpBody {
+    template <class MP>
+    static MPCF_DI void run(const MP &m, long u, long U, EeArgs ee, double wsign, const double *q, const double *qd,
+                            const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd)
+    {
+        constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
+        using D = Dyn<Dual, MP>;
+        const int n = m.n();
+        const int d = blockIdx.y;
+        Dual a[MP::MAXN], b[MP::MAXN], c[MP::MAXN], t[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) {
+            a[i] = Dual(q[i * U + u], d == i ? 1.0 : 0.0);
+            b[i] = Dual(qd[i * U + u], d == n + i ? 1.0 : 0.0);
+            c[i] = Dual(qdd ? qdd[i * U + u] : 0.0, 0.0);
+        }
+        JointVar<Dual> jv[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) D::joint_var(m, i, a[i], jv[i]);
+        D::rnea_jv(m, jv, b, c, t);
+        if (ee.nee > 0 && d < n) {  // J^T W depends on q only
+            Dual oR[MP::MAXN][9], op[MP::MAXN][3];
+            D::fk_all_jv(m, jv, oR, op);
+            for (int e = 0; e < ee.nee; ++e) {
+                Dual pf[3], Rf[9];
+                D::frame_pose(ee.f[e].joint, ee.f[e].R, ee.f[e].p, oR, op, pf, Rf);
+                double w[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) w[r] = W[(long)(6 * e + r) * U + u];
+                int cur = ee.f[e].joint;
+#pragma unroll UNR
+                for (int i = n - 1; i >= 0; --i) {
+                    if (i == cur) {
+                        const Dual z[3] = {oR[i][2], oR[i][5], oR[i][8]};
+                        Dual acc;
+                        if (!m.prismatic(i)) {
+                            const Dual dd[3] = {pf[0] - op[i][0], pf[1] - op[i][1], pf[2] - op[i][2]};
+                            Dual lin[3];
+                            cross3(z, dd, lin);
+                            acc = lin[0] * w[0] + lin[1] * w[1] + lin[2] * w[2] + z[0] * w[3] + z[1] * w[4] + z[2] * w[5];
+                        } else {
+                            acc = z[0] * w[0] + z[1] * w[1] + z[2] * w[2];
+                        }
+                        t[i] += wsign * acc;
+                        cur = m.parent(i);
+                    }
+                }
+            }
+        }
+        double *out = d < n ? dtau_dq : dtau_dqd;
+        const int col = d % n;
+#pragma unroll UNR
+        for (int r = 0; r < n; ++r) out[(size_t)(r * n + col) * U + u] = t[r].d;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // per-scenario cost / residual reduction: thread b walks the N nodes of scenario b (u = k*B + b,
 // coalesced across b) and writes (cost, defect, torque-bound, fatigue-bound) into out[4][B]
@@ -216,6 +276,11 @@ cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsig
                              double *qnext, double *Tnext, bool jtw_only, cudaStream_t s)
 {
     return dispatch<NodeEvalBody>(m, U, 1, s, ee, wsign, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, jtw_only);
+}
+cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                                 const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
+{
+    return dispatch<NodeEvalJvpBody>(m, U, 2 * m.n, s, ee, wsign, q, qd, qdd, W, dtau_dq, dtau_dqd);
 }
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
                                  const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,

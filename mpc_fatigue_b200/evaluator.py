@@ -112,6 +112,20 @@ class BatchEvaluator:
                 float(h), p(tau), p(qn), p(Tn), _stream()))
         return tau, qn, Tn
 
+    def node_eval_ref_jvp(self, ee_frames, wsign: float, q, qd, W=None, qdd=None):
+        """d tau/d q, d tau/d qd ([n*n, U], plane row*n + col) of the reference-mode torque
+        tau = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e;  d tau/d W_e = wsign * J_e^T (see `jacobian`)."""
+        U, n = self._U(q), self.n
+        nee = len(ee_frames)
+        fr = (C.c_int * max(nee, 1))(*[int(f) for f in ee_frames])
+        Dq, Dv = self._out(None, n * n, U, "dtau_dq"), self._out(None, n * n, U, "dtau_dqd")
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_node_eval_ref_jvp_batch(
+                self.model.handle, nee, fr, float(wsign), U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"),
+                self._in(qdd, n, U, "qdd", True), self._in(W, 6 * nee, U, "W", nee == 0), C.c_void_p(Dq.data_ptr()),
+                C.c_void_p(Dv.data_ptr()), _stream()))
+        return Dq, Dv
+
     # ---- north-star additions ----
     def aba(self, q, qd, tau, out=None):
         U, n = self._U(q), self.n

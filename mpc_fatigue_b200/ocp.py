@@ -115,6 +115,22 @@ class PilzForceOCP:
         }
 
 
+    def jacobian(self, q: torch.Tensor, qd: torch.Tensor, Fx: torch.Tensor) -> dict:
+        """First derivatives of the g-rows of `evaluate` with respect to the node's own decision variables
+        (what IPOPT's `jac_g` needs; CasADi derives them from the SX graph in the reference):
+          dtau_dq, dtau_dqd [B, N, 6, 6];  dtau_dFx [B, N, 6] = -J[0, :];  dline_dq [B, N, 2, 6] = J[0:2, :];
+          the Euler defect q_k + h qd_k - q_{k+1} has constant blocks (I, h I, -I)."""
+        B, N, n = qd.shape
+        ev = self.rf.ev
+        qk = q[:, :N]
+        W = torch.zeros((B, N, 6), dtype=torch.float64, device=q.device)
+        W[..., 0] = Fx
+        Dq, Dv = ev.node_eval_ref_jvp([self.frame], -1.0, _soa(qk), _soa(qd), _soa(W))
+        J = _aos(ev.jacobian(self.frame, _soa(qk)), (B, N)).reshape(B, N, 6, n)
+        return {"dtau_dq": _aos(Dq, (B, N)).reshape(B, N, n, n), "dtau_dqd": _aos(Dv, (B, N)).reshape(B, N, n, n),
+                "dtau_dFx": -J[:, :, 0, :], "dline_dq": J[:, :, 0:2, :], "defect_dq": 1.0, "defect_dqd": self.h, "defect_dqnext": -1.0}
+
+
 class DualArmBoxOCP:
     """Dual-arm box OCP (python/2_pilz_6_DOF/Box_Pilz_6DOF2.py): two separate 6-DOF models.
 

@@ -276,3 +276,26 @@ int mpcfo_rnea_derivs_batch(const mpcfo_model *m, long U, const double *q, const
     }
     return 0;
 }
+
+/* d tau/d q and d tau/d qd of the reference-mode torque tau = RNEA + wsign * sum J^T W, complex-step through node_eval_ref_c */
+int mpcfo_node_eval_ref_jvp_batch(const mpcfo_model *m, int nee, const int *ee_frames, double wsign, long U, const double *q,
+                                  const double *qd, const double *qdd, const double *W, double *Dq, double *Dv)
+{
+    CHECK_N(m);
+    if (nee < 0 || nee > 8) return -2;
+    const int n = m->n;
+    const double hstep = 1e-40;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        double complex a[MPCFO_MAXN], b[MPCFO_MAXN], c[MPCFO_MAXN], Tl[MPCFO_MAXN], Wl[48], t[MPCFO_MAXN], qn[MPCFO_MAXN], Tn[MPCFO_MAXN];
+        for (int d = 0; d < 2 * n; ++d) {
+            for (int i = 0; i < n; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; Tl[i] = 0.0; }
+            for (int k = 0; k < 6 * nee; ++k) Wl[k] = W[k * U + u];
+            if (d < n) a[d] += hstep * I; else b[d - n] += hstep * I;
+            node_eval_ref_c(m, nee, ee_frames, wsign, a, b, c, Wl, Tl, 0.0, t, qn, Tn);
+            double *out = d < n ? Dq : Dv;
+            for (int r = 0; r < n; ++r) out[((long)r * n + d % n) * U + u] = cimag(t[r]) / hstep;
+        }
+    }
+    return 0;
+}

@@ -69,6 +69,9 @@ int mpcfo_fd_derivs_batch(const mpcfo_model *m, long U, const double *q, const d
 int mpcfo_rnea_derivs_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
                             double *Dq, double *Dv, double *M);
 
+int mpcfo_node_eval_ref_jvp_batch(const mpcfo_model *m, int nee, const int *ee_frames, double wsign, long U, const double *q,
+                                  const double *qd, const double *qdd, const double *W, double *Dq, double *Dv);
+
 #ifdef __cplusplus
 }
 #endif

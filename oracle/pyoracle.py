@@ -179,3 +179,16 @@ class Oracle:
                                               _p(qdd if qdd is None else _chk(qdd, n, U)), _p(Dq), _p(Dv), _p(M))
         assert rc == 0, rc
         return Dq, Dv, M
+
+    def node_eval_ref_jvp(self, ee_frames, wsign, q, qd, W, qdd=None):
+        """d tau/d q, d tau/d qd of tau = RNEA + wsign * sum J^T W as [n*n, U] planes."""
+        n, U = q.shape
+        nee = len(ee_frames)
+        fr = (C.c_int * max(nee, 1))(*ee_frames)
+        Dq, Dv = np.empty((n * n, U)), np.empty((n * n, U))
+        if W is None:
+            W = np.zeros((6 * max(nee, 1), U))
+        rc = self.lib.mpcfo_node_eval_ref_jvp_batch(self._ref(), nee, fr, C.c_double(wsign), C.c_long(U), _p(_chk(q, n, U)),
+                                                    _p(_chk(qd, n, U)), _p(qdd), _p(W), _p(Dq), _p(Dv))
+        assert rc == 0, rc
+        return Dq, Dv

@@ -97,6 +97,49 @@ def test_function_lookalike_matches_oracle(torch_mod):
     assert Jd.shape == (4, 18, 25) and rel_err(Jd, np.moveaxis(rj, 2, 0)) < TOL
 
 
+def test_pilz_force_ocp_rows_and_their_jacobian(torch_mod):
+    """The batched 6-DOF force OCP (force_optimization_pilz_6DOF.py:103-178): g-rows vs the oracle, and the Jacobian
+    blocks an NLP solver needs vs central differences of the rows themselves."""
+    torch = torch_mod
+    from mpc_fatigue_b200.model import data_urdf
+    from mpc_fatigue_b200.ocp import PilzForceOCP
+    from oracle.pyoracle import Oracle
+    from oracle.urdf_model import load_urdf
+    xml = data_urdf("pilz6")
+    ocp = PilzForceOCP(xml, frame="prbt_link_5", N=6, T=2.0)
+    om = load_urdf(xml)
+    orc = Oracle(om)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, N = 4, 6
+    q = (torch.rand((B, N + 1, 6), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 3.0
+    qd = (torch.rand((B, N, 6), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 2.0
+    Fx = (torch.rand((B, N), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 80.0
+    rows = ocp.evaluate(q, qd, Fx, ref_xy=(0.1, 0.2))
+    # rows against the oracle
+    c = lambda t: np.ascontiguousarray(t.reshape(-1, t.shape[-1]).T.cpu().numpy())
+    W = np.zeros((6, B * N)); W[0] = Fx.reshape(-1).cpu().numpy()
+    fr = om.frame_id("prbt_link_5")
+    rt, rqn, _ = orc.node_eval_ref([fr], -1.0, c(q[:, :N]), c(qd), W, np.zeros((6, B * N)), ocp.h)
+    assert rel_err(c(rows["tau"]), rt) < TOL
+    assert rel_err(c(rows["defect"]), rqn - c(q[:, 1:])) < TOL
+    pos, _ = orc.fk(fr, c(q[:, :N]))
+    assert rel_err(c(rows["line"]), pos[:2] - np.array([[0.1], [0.2]])) < TOL
+    assert rows["tau_bound"][0] == 50.0 and float(rows["cost"][0]) == float(-(Fx[0] ** 2).sum())
+    # Jacobian blocks against central differences of the rows
+    jac = ocp.jacobian(q, qd, Fx)
+    eps = 1e-6
+    for j in range(6):
+        dq = torch.zeros_like(q); dq[:, :N, j] = eps
+        rp, rm = ocp.evaluate(q + dq, qd, Fx, (0.1, 0.2)), ocp.evaluate(q - dq, qd, Fx, (0.1, 0.2))
+        assert float(((rp["tau"] - rm["tau"]) / (2 * eps) - jac["dtau_dq"][..., j]).abs().max()) < 2e-5
+        assert float(((rp["line"] - rm["line"]) / (2 * eps) - jac["dline_dq"][..., j]).abs().max()) < 1e-7
+        dv = torch.zeros_like(qd); dv[..., j] = eps
+        rp, rm = ocp.evaluate(q, qd + dv, Fx, (0.1, 0.2)), ocp.evaluate(q, qd - dv, Fx, (0.1, 0.2))
+        assert float(((rp["tau"] - rm["tau"]) / (2 * eps) - jac["dtau_dqd"][..., j]).abs().max()) < 2e-6
+    rp, rm = ocp.evaluate(q, qd, Fx + eps, (0.1, 0.2)), ocp.evaluate(q, qd, Fx - eps, (0.1, 0.2))
+    assert float(((rp["tau"] - rm["tau"]) / (2 * eps) - jac["dtau_dFx"]).abs().max()) < 1e-7
+
+
 def test_singular_forward_dynamics_is_an_error_not_a_nan(torch_mod):
     torch = torch_mod
     from mpc_fatigue_b200.evaluator import BatchEvaluator

@@ -87,6 +87,29 @@ def test_jac_t_wrench_and_node_eval(setup):
     assert rel_err(got, ref) < TOL
 
 
+def test_node_eval_ref_jvp(setup):
+    """Jacobian blocks of the reference-mode torque rows vs complex-step through the oracle's node evaluation."""
+    torch = setup["torch"]
+    q, qd, tau, f, qdd = setup["host"]
+    dq, dqd, dtau, df, dqdd = setup["dev"]
+    m = setup["m"]
+    U = min(setup["U"], 40)
+    rng = np.random.default_rng(6)
+    ee = [m.nframes - 1] if m.n != 12 else [m.frame_id("end_effector"), m.frame_id("sec_end_effector")]
+    W = np.ascontiguousarray(rng.uniform(-50, 50, (6 * len(ee), U)))
+    sl = lambda a: np.ascontiguousarray(a[:, :U])
+    dsl = lambda a: a[:, :U].contiguous()
+    for wsign in (-1.0, 1.0):
+        rDq, rDv = setup["orc"].node_eval_ref_jvp(ee, wsign, sl(q), sl(qd), W, qdd=sl(qdd))
+        gDq, gDv = setup["ev"].node_eval_ref_jvp(ee, wsign, dsl(dq), dsl(dqd), torch.from_numpy(W).cuda(), qdd=dsl(dqdd))
+        assert rel_err(gDq.cpu().numpy(), rDq) < TOL
+        assert rel_err(gDv.cpu().numpy(), rDv) < TOL
+    # without wrenches it reduces to the inverse-dynamics derivatives
+    gDq0, gDv0 = setup["ev"].node_eval_ref_jvp([], 1.0, dsl(dq), dsl(dqd), None, qdd=dsl(dqdd))
+    aDq, aDv, _ = setup["ev"].rnea_derivs(dsl(dq), dsl(dqd), dsl(dqdd))
+    assert rel_err(gDq0.cpu().numpy(), aDq.cpu().numpy()) < 1e-10 and rel_err(gDv0.cpu().numpy(), aDv.cpu().numpy()) < 1e-10
+
+
 def test_aba(setup):
     q, qd, tau, f, qdd = setup["host"]
     dq, dqd, dtau, df, dqdd = setup["dev"]
