@@ -42,3 +42,18 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 print("%s: U=%d  %.3f ms/launch  %.3e units/s" % (which, U, ms, U / ms * 1e3))
+if which == "nodejvp":
+    import time
+    for r in range(reps + 1):
+        if r == 1:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        ev.node_eval_ref_jvp([fr], -1.0, q, qd, W)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    print("nodejvp: U=%d  %.3f ms/launch  %.3e units/s" % (U, ms, U / ms * 1e3))
+    ev.rnea_derivs(q, qd); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for r in range(reps):
+        ev.rnea_derivs(q, qd)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    print("rnea_derivs: U=%d  %.3f ms/launch  %.3e units/s" % (U, ms, U / ms * 1e3))
