@@ -67,6 +67,8 @@ typedef struct {
 #define MPCF_SYNTH_HUMANOID 1   /* floating-base-like branched tree: 3 prismatic + 3 revolute root chain,
                                    1 torso joint, 2 arms x 7, 4 legs x 4 (37 DOF when ndof = 37) */
 
+#define MPCF_SYNTH_DUAL_ARM 2    /* two serial revolute arms of ndof/2 joints on a fixed torso (Centauro layout: 2 x 7) */
+
 void mpcf_opts_default(mpcf_opts *opts);
 
 int mpcf_model_create_from_urdf(const char *xml, size_t len, const mpcf_opts *opts, mpcf_model **out);

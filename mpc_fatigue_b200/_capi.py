@@ -19,7 +19,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 OK, EINVAL, EPARSE, EJOINT, EFRAME, ESINGULAR, ECUDA, ELIMIT = 0, -1, -2, -3, -4, -5, -6, -7
-SYNTH_CHAIN, SYNTH_HUMANOID = 0, 1
+SYNTH_CHAIN, SYNTH_HUMANOID, SYNTH_DUAL_ARM = 0, 1, 2
 MAX_DOF, MAX_EE = 64, 4
 
 

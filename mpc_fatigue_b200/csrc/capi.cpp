@@ -17,6 +17,8 @@ struct mpcf_model {
     // static-family parameter block (largest variant), filled for the family in use
     StaticParams<12> sp12;
     StaticParams<6> chain6[2];  // forest12x6: the two arms as stand-alone 6-DOF chains
+    StaticParams<14> sp14;
+    StaticParams<7> sp7, chain7[2];  // chain7 / forest14x7 (the reference's Centauro layout: 2 x 7 arms)
     StaticParams<6> sp6;
     StaticParams<3> sp3;
     // device copy of the generic blob, uploaded lazily on first launch (model creation needs no GPU)
@@ -50,17 +52,19 @@ extern "C" void mpcf_opts_default(mpcf_opts *o)
     o->cv = 1.0 / Rh;
 }
 
+// joints [first, first + N) of the host model as a stand-alone parameter block
 template <int N>
-static void fill_static(const HostModel &h, StaticParams<N> &p)
+static void fill_static(const HostModel &h, StaticParams<N> &p, int first = 0)
 {
     for (int i = 0; i < N; ++i) {
-        std::memcpy(p.Rp[i], &h.Rp[9 * i], 9 * sizeof(double));
-        std::memcpy(p.pp[i], &h.pp[3 * i], 3 * sizeof(double));
-        p.mass[i] = h.mass[i];
-        std::memcpy(p.mc[i], &h.mc[3 * i], 3 * sizeof(double));
-        std::memcpy(p.Io[i], &h.Io[6 * i], 6 * sizeof(double));
-        p.arm[i] = h.arm[i];
-        std::memcpy(p.fat[i], &h.fat[4 * i], 4 * sizeof(double));
+        const int g = first + i;
+        std::memcpy(p.Rp[i], &h.Rp[9 * g], 9 * sizeof(double));
+        std::memcpy(p.pp[i], &h.pp[3 * g], 3 * sizeof(double));
+        p.mass[i] = h.mass[g];
+        std::memcpy(p.mc[i], &h.mc[3 * g], 3 * sizeof(double));
+        std::memcpy(p.Io[i], &h.Io[6 * g], 6 * sizeof(double));
+        p.arm[i] = h.arm[g];
+        std::memcpy(p.fat[i], &h.fat[4 * g], 4 * sizeof(double));
     }
     std::memcpy(p.grav, h.grav, sizeof p.grav);
 }
@@ -83,20 +87,13 @@ static void refresh(mpcf_model *m)
     else if (h.n == 12 && is_forest(h, 6)) {
         m->fam = FAM_FOREST12x6;
         fill_static(h, m->sp12);
-        for (int c = 0; c < 2; ++c) {
-            StaticParams<6> &p = m->chain6[c];
-            for (int i = 0; i < 6; ++i) {
-                const int g = 6 * c + i;
-                std::memcpy(p.Rp[i], m->sp12.Rp[g], sizeof p.Rp[i]);
-                std::memcpy(p.pp[i], m->sp12.pp[g], sizeof p.pp[i]);
-                p.mass[i] = m->sp12.mass[g];
-                std::memcpy(p.mc[i], m->sp12.mc[g], sizeof p.mc[i]);
-                std::memcpy(p.Io[i], m->sp12.Io[g], sizeof p.Io[i]);
-                p.arm[i] = m->sp12.arm[g];
-                std::memcpy(p.fat[i], m->sp12.fat[g], sizeof p.fat[i]);
-            }
-            std::memcpy(p.grav, m->sp12.grav, sizeof p.grav);
-        }
+        for (int c = 0; c < 2; ++c) fill_static(h, m->chain6[c], 6 * c);
+    }
+    else if (h.n == 7 && is_forest(h, 7)) { m->fam = FAM_CHAIN7; fill_static(h, m->sp7); }
+    else if (h.n == 14 && is_forest(h, 7)) {
+        m->fam = FAM_FOREST14x7;
+        fill_static(h, m->sp14);
+        for (int c = 0; c < 2; ++c) fill_static(h, m->chain7[c], 7 * c);
     }
     else m->fam = h.n <= 16 ? FAM_GENERIC16 : FAM_GENERIC64;
     m->dirty = true;
@@ -188,6 +185,8 @@ extern "C" const char *mpcf_model_kernel_family(const mpcf_model *m)
     case FAM_CHAIN3: return "chain3";
     case FAM_CHAIN6: return "chain6";
     case FAM_FOREST12x6: return "forest12x6";
+    case FAM_CHAIN7: return "chain7";
+    case FAM_FOREST14x7: return "forest14x7";
     case FAM_GENERIC16: return "generic16";
     default: return "generic64";
     }
@@ -260,6 +259,8 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
     case FAM_CHAIN3: lm.static_params = &m->sp3; return MPCF_OK;
     case FAM_CHAIN6: lm.static_params = &m->sp6; return MPCF_OK;
     case FAM_FOREST12x6: lm.static_params = &m->sp12; lm.chain_params = m->chain6; return MPCF_OK;
+    case FAM_CHAIN7: lm.static_params = &m->sp7; return MPCF_OK;
+    case FAM_FOREST14x7: lm.static_params = &m->sp14; lm.chain_params = m->chain7; return MPCF_OK;
     default: break;
     }
     std::lock_guard<std::mutex> lk(m->mu);
@@ -467,7 +468,7 @@ extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, lon
     if (!jvp2_supported(lm)) return 0;
     long units = U < kJvpChunkUnits ? U : kJvpChunkUnits;
     units = (units + 31) / 32 * 32;
-    const int nchain = model->fam == FAM_FOREST12x6 ? 6 : model->h.n;  // forests run one chain at a time
+    const int nchain = family_chain_len(model->fam);  // forests run one chain at a time
     return (size_t)units * jvp_ws_doubles_per_unit(nchain) * sizeof(double);
 }
 
@@ -478,7 +479,7 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
     PROLOGUE(q && qd && tau && f && jac)
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
-    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(model->fam == FAM_FOREST12x6 ? 6 : model->h.n) * sizeof(double);
+    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
     if (!jvp2_supported(lm) || !workspace || workspace_bytes < min_ws)  // no workspace path: direct dual-number kernel
         return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
     if (reinterpret_cast<uintptr_t>(workspace) % 8) return fail(MPCF_EINVAL, "workspace must be 8-byte aligned");

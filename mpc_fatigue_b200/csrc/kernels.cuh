@@ -39,7 +39,10 @@ struct ZohArg {
     double a[MPCF_MAX_DOF];  // exp(-lambda_i h), computed once on the host
 };
 
-enum Family { FAM_GENERIC16 = 0, FAM_GENERIC64, FAM_CHAIN3, FAM_CHAIN6, FAM_FOREST12x6, FAM_COUNT };
+enum Family { FAM_GENERIC16 = 0, FAM_GENERIC64, FAM_CHAIN3, FAM_CHAIN6, FAM_FOREST12x6, FAM_CHAIN7, FAM_FOREST14x7, FAM_COUNT };
+// serial-chain length of a static family (0 for run-time-topology families) and number of chains
+inline int family_chain_len(Family f) { return f == FAM_CHAIN3 ? 3 : (f == FAM_CHAIN6 || f == FAM_FOREST12x6) ? 6 : (f == FAM_CHAIN7 || f == FAM_FOREST14x7) ? 7 : 0; }
+inline int family_chains(Family f) { return (f == FAM_FOREST12x6 || f == FAM_FOREST14x7) ? 2 : (family_chain_len(f) ? 1 : 0); }
 
 struct LaunchModel {
     Family fam;

@@ -543,8 +543,12 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * N * kThreads * (int)sizeof(double));
+            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
+            if (N <= 6) {
+                e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * N * kThreads * (int)sizeof(double));
+                if (e != cudaSuccess) return e;
+            }
             attr_set[dev] = true;
         }
     }
@@ -557,7 +561,7 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         prof_end(s);
         prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
-        if (k2smem && N <= 6) {  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
+        if (k2smem && N <= 6) {  // (N = 7: 129 KB per block would leave one block per SM)  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
             constexpr int slab = 18 * N * kThreads * (int)sizeof(double);
             k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
         } else {
@@ -567,8 +571,9 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         prof_begin(2, s);
         if constexpr (N <= 6) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
-            static const int cpw = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
-            if (cpw == 2) k_chain_rule_tma<N, L, NBUF, 2, true><<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            static const int cpw_env = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
+            const int cpw = (3 * N + 1 > 19) ? 2 : cpw_env;  // more than 19 columns: two per thread (register file)
+            if (cpw == 2) (ntot == N ? k_chain_rule_tma<N, L, NBUF, 2, true> : k_chain_rule_tma<N, L, NBUF, 2, false>)<<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
             else if (ntot == N) k_chain_rule_tma<N, L, NBUF, 1, true><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
             else k_chain_rule_tma<N, L, NBUF, 1, false><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
         } else {
@@ -580,14 +585,30 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
     return cudaGetLastError();
 }
 
-bool jvp2_supported(const LaunchModel &m) { return m.fam == FAM_CHAIN3 || m.fam == FAM_CHAIN6 || m.fam == FAM_FOREST12x6; }
+// Forests: the chains are dynamically decoupled, so each runs the single-chain pipeline on its own input planes and writes its
+// block of the whole-model Jacobian (plus the zeros of the cross blocks).
+template <int L>
+static cudaError_t run_forest(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f, double dt,
+                              const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws, long Uc, cudaStream_t s)
+{
+    const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.chain_params);
+    for (int c = 0; c < m.n / L; ++c) {
+        const size_t off = (size_t)c * L * U;
+        cudaError_t e = run_jvp2<L, L>(cp[c], U, q + off, qd + off, tau + off, f + off, dt, dt_u, qn ? qn + off : nullptr,
+                                       qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, ws, Uc, s, m.n, L * c);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+bool jvp2_supported(const LaunchModel &m) { return family_chain_len(m.fam) > 0; }
 
 cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                                double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws,
                                size_t ws_bytes, cudaStream_t s)
 {
     if (U <= 0) return cudaSuccess;
-    const size_t per_unit = jvp_ws_doubles_per_unit(m.fam == FAM_FOREST12x6 ? 6 : m.n) * sizeof(double);
+    const size_t per_unit = jvp_ws_doubles_per_unit(family_chain_len(m.fam)) * sizeof(double);
     long Uc = (long)(ws_bytes / per_unit);
     Uc -= Uc % 32;  // whole 32-unit tiles
     if (Uc < 32) return cudaErrorInvalidValue;
@@ -596,20 +617,12 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
         return run_jvp2<3, 3>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
     case FAM_CHAIN6:
         return run_jvp2<6, 6>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+    case FAM_CHAIN7:
+        return run_jvp2<7, 7>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
     case FAM_FOREST12x6:
-    {   // the chains are dynamically decoupled: one 6-DOF pipeline per chain on its own input planes, writing its block
-        // of the 36 x 49 Jacobian (and the zeros of the cross blocks)
-        const StaticParams<6> *cp = static_cast<const StaticParams<6> *>(m.chain_params);
-        Uc = (long)(ws_bytes / (jvp_ws_doubles_per_unit(6) * sizeof(double)));
-        Uc -= Uc % 32;
-        for (int c = 0; c < 2; ++c) {
-            const size_t off = (size_t)c * 6 * U;
-            cudaError_t e = run_jvp2<6, 6>(cp[c], U, q + off, qd + off, tau + off, f + off, dt, dt_u, qn ? qn + off : nullptr,
-                                           qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, ws, Uc, s, 12, 6 * c);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    }
+        return run_forest<6>(m, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+    case FAM_FOREST14x7:
+        return run_forest<7>(m, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
     default:
         return cudaErrorInvalidValue;
     }
@@ -626,6 +639,9 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
         break;
     case FAM_CHAIN6:
         k_rnea_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        break;
+    case FAM_CHAIN7:
+        k_rnea_derivs<7, 7><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
         break;
     default:
         return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
@@ -646,8 +662,8 @@ cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, cons
     case FAM_CHAIN6:
         k_fd_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, A, B, C);
         break;
-    case FAM_FOREST12x6:
-        k_fd_derivs<12, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<12> *>(m.static_params), U, q, qd, tau, A, B, C);
+    case FAM_CHAIN7:
+        k_fd_derivs<7, 7><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, tau, A, B, C);
         break;
     default:
         return dispatch<FdDerivsDualBody>(m, U, 3 * m.n, s, q, qd, tau, A, B, C);

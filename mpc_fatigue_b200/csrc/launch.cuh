@@ -103,6 +103,12 @@ static cudaError_t dispatch(const LaunchModel &m, long U, int grid_y, cudaStream
     case FAM_FOREST12x6:
         static_kernel<12, 6, Body, Args...><<<grid, block, 0, s>>>(*static_cast<const StaticParams<12> *>(m.static_params), U, args...);
         break;
+    case FAM_CHAIN7:
+        static_kernel<7, 7, Body, Args...><<<grid, block, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, args...);
+        break;
+    case FAM_FOREST14x7:
+        static_kernel<14, 7, Body, Args...><<<grid, block, 0, s>>>(*static_cast<const StaticParams<14> *>(m.static_params), U, args...);
+        break;
     case FAM_GENERIC16:
         generic_kernel<16, Body, Args...><<<grid, block, blob_smem_bytes(m.n), s>>>(m.blob, U, args...);
         break;

@@ -429,6 +429,20 @@ int make_synthetic(int kind, int ndof, unsigned long long seed, const mpcf_opts 
         for (int i = 0; i < ndof; ++i) par = add_random_link(m, r, par, "joint_" + std::to_string(i + 1), opts, 0.3, 1.0);
         return MPCF_OK;
     }
+    if (kind == MPCF_SYNTH_DUAL_ARM) {  // two serial arms of ndof/2 joints on a fixed torso (the reference's Centauro layout: 2 x 7)
+        if (ndof % 2) { err = "dual-arm model needs an even ndof"; return MPCF_EINVAL; }
+        const char *side[2] = {"left", "right"};
+        for (int a = 0; a < 2; ++a) {
+            int par = -1;
+            for (int i = 0; i < ndof / 2; ++i) {
+                par = add_random_link(m, r, par, std::string(side[a]) + "_joint_" + std::to_string(i + 1), opts, 0.3, 1.0);
+                if (i == 0) m.pp[3 * par + 1] += a == 0 ? 0.25 : -0.25;  // shoulders 0.5 m apart
+            }
+            double pe[3] = {0, 0, 0.1};
+            m.add_frame(std::string(side[a]) + "_ee", par, kEye, pe);
+        }
+        return MPCF_OK;
+    }
     if (kind != MPCF_SYNTH_HUMANOID) { err = "unknown synthetic kind"; return MPCF_EINVAL; }
     if (ndof < 8) { err = "humanoid tree needs ndof >= 8"; return MPCF_EINVAL; }
     // floating base as a root chain with nq = nv: prismatic x, y, z then revolute z, y, x.

@@ -59,7 +59,7 @@ class Model:
 
     @classmethod
     def synthetic(cls, kind: str, ndof: int, seed: int = 1, armature: float = 0.0, **kw) -> "Model":
-        kinds = {"chain": _capi.SYNTH_CHAIN, "humanoid": _capi.SYNTH_HUMANOID}
+        kinds = {"chain": _capi.SYNTH_CHAIN, "humanoid": _capi.SYNTH_HUMANOID, "dual_arm": _capi.SYNTH_DUAL_ARM}
         if kind not in kinds:
             raise ValueError("unknown synthetic kind %r" % kind)
         opts = make_opts(armature=armature, **kw)

@@ -15,6 +15,8 @@ CASES = [
     ("pilz3", dict(urdf="pilz3", armature=0.0)),
     ("pilz6x2", dict(urdf="pilz6x2", armature=1e-2)),
     ("pilz6_second", dict(urdf="pilz6_second", armature=1e-2)),
+    ("chain7", dict(synthetic=("chain", 7, 2), armature=1e-3)),
+    ("dualarm14", dict(synthetic=("dual_arm", 14, 4), armature=1e-2)),
     ("chain10", dict(synthetic=("chain", 10, 3), armature=1e-3)),
     ("humanoid37", dict(synthetic=("humanoid", 37, 7), armature=1e-2)),
 ]

@@ -87,6 +87,19 @@ def test_synthetic_humanoid_tree():
     assert not np.array_equal(m.export("Rp"), Model.synthetic("humanoid", 37, seed=8).export("Rp"))
 
 
+def test_synthetic_dual_arm_and_static_families():
+    m = Model.synthetic("dual_arm", 14, seed=4, armature=1e-2)  # the reference's Centauro layout: two 7-DOF arms
+    assert m.n == 14 and m.kernel_family == "forest14x7"
+    assert m.export("parent").tolist() == [-1, 0, 1, 2, 3, 4, 5, -1, 7, 8, 9, 10, 11, 12]
+    assert m.joint_names[0] == "left_joint_1" and m.joint_names[7] == "right_joint_1"
+    assert m.frame_id("left_ee") >= 0 and m.frame_id("right_ee") >= 0
+    assert Model.synthetic("dual_arm", 12).kernel_family == "forest12x6"
+    assert Model.synthetic("dual_arm", 10).kernel_family == "generic16"
+    assert Model.synthetic("chain", 7).kernel_family == "chain7"
+    with pytest.raises(ValueError):
+        Model.synthetic("dual_arm", 13)
+
+
 def test_setters_update_model():
     m = Model.from_urdf(data_urdf("pilz6"))
     m.set_armature(0.02)
