@@ -63,6 +63,8 @@ cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const do
 cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                              const double *qdd, const double *W, const double *T, double h, const ZohArg &zoh, double *tau,
                              double *qnext, double *Tnext, bool jtw_only, cudaStream_t s);
+cudaError_t launch_node_eval_jvp_dual(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                                      const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s);
 cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                                  const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s);
 cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *qdd, cudaStream_t s);

@@ -277,7 +277,7 @@ cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsig
 {
     return dispatch<NodeEvalBody>(m, U, 1, s, ee, wsign, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, jtw_only);
 }
-cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+cudaError_t launch_node_eval_jvp_dual(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                                  const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
 {
     return dispatch<NodeEvalJvpBody>(m, U, 2 * m.n, s, ee, wsign, q, qd, qdd, W, dtau_dq, dtau_dqd);

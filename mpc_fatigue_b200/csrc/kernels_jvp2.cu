@@ -163,6 +163,91 @@ __global__ void __launch_bounds__(kThreads) k_rnea_derivs(const __grid_constant_
     FdDerivs<StaticModel<N, L>, L>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
 }
 
+// Reference-mode torque rows tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e (force_optimization_pilz_6DOF.py:134,
+// Box_Pilz_6DOF2.py:292-293, mpc_principal.py:269), first derivatives w.r.t. q and qd, analytic, thread = unit.
+// ID part: the world-frame pairing pass of derivs.cuh.  External part: with S_i = [o_i x z_i ; z_i] and the wrench moved to the
+// world origin, Wo = [F ; n + p_f x F] (F, n fixed in world axes, p_f attached to the frame's link),
+//   J_e^T W |_i = S_i . Wo,    d/dq_j = [j < i] (S_j x S_i) . Wo + ang(S_i) . ((lin(S_j) + ang(S_j) x p_f) x F),   i, j on the path to e
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_node_eval_jvp(const __grid_constant__ StaticParams<N> P, long U, EeArgs ee, double wsign,
+                                                           const double *q, const double *qd, const double *qdd, const double *W,
+                                                           double *Dq, double *Dv, int ntot, int c0)
+{
+    // one serial chain of N joints = joints [c0, c0 + N) of an ntot-joint forest (q, qd, qdd already point at the chain's planes)
+    const StaticModel<N, N> m{P};
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double a[N], b[N], c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
+    LocalLinkStore<N> ks;
+    double dq[N][N];
+    auto emit = [&](int mat, int r, int cc, double v) {
+        if (mat == 0) dq[r][cc] = v;
+        else if (mat == 1) Dv[(size_t)((c0 + r) * ntot + c0 + cc) * U + u] = v;
+    };
+    FdDerivs<StaticModel<N, N>, N>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
+    if (ee.nee > 0) {
+        double oR[N][9], op[N][3];
+        Dyn<double, StaticModel<N, N>>::fk_all(m, a, oR, op);
+#pragma unroll 1
+        for (int e = 0; e < ee.nee; ++e) {
+            const int je = ee.f[e].joint - c0;
+            if (ee.f[e].joint < 0 || je < 0 || je >= N) continue;  // frame fixed to the world or carried by another chain
+            double pf[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i == je) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        pf[r] = op[i][r] + oR[i][3 * r] * ee.f[e].p[0] + oR[i][3 * r + 1] * ee.f[e].p[1] + oR[i][3 * r + 2] * ee.f[e].p[2];
+                }
+            double Wo[6], F[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { F[r] = W[(long)(6 * e + r) * U + u]; Wo[r] = F[r]; }
+            cross3(pf, F, Wo + 3);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Wo[3 + r] += W[(long)(6 * e + 3 + r) * U + u];
+            double hj[N][3];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                LinkFwd Kj;
+                ks.get(j, Kj);
+                double t[3], dp[3];
+                cross3(Kj.S + 3, pf, t);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) dp[r] = Kj.S[r] + t[r];
+                cross3(dp, F, hj[j]);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                LinkFwd Ki;
+                ks.get(i, Ki);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double val = dot3(Ki.S + 3, hj[j]);
+                    if (j < i) {
+                        LinkFwd Kj;
+                        ks.get(j, Kj);
+                        double x[6];
+                        mxm(Kj.S, Ki.S, x);
+                        val += dot6(x, Wo);
+                    }
+                    if (i <= je && j <= je) dq[i][j] += wsign * val;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+#pragma unroll
+        for (int cc = 0; cc < N; ++cc) Dq[(size_t)((c0 + r) * ntot + c0 + cc) * U + u] = dq[r][cc];
+#pragma unroll 1
+        for (int cc = 0; cc < ntot; ++cc)  // entries between different chains are structurally zero
+            if (cc < c0 || cc >= c0 + N) { Dq[(size_t)((c0 + r) * ntot + cc) * U + u] = 0.0; Dv[(size_t)((c0 + r) * ntot + cc) * U + u] = 0.0; }
+    }
+}
+
 // generic fallback: one dual-number RNEA sweep per seed direction (blockIdx.y in [0, 3n): q, qd, qdd seeds)
 struct RneaDerivsDualBody {
     template <class MP>
@@ -628,6 +713,33 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
     }
 }
 
+template <int L>
+static cudaError_t node_eval_jvp_chains(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                                        const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
+{
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params);
+    for (int c = 0; c < m.n / L; ++c) {
+        const size_t off = (size_t)c * L * U;
+        k_node_eval_jvp<L><<<gb, kThreads, 0, s>>>(cp[c], U, ee, wsign, q + off, qd + off, qdd ? qdd + off : nullptr, W, dtau_dq, dtau_dqd,
+                                                    m.n, c * L);
+        g_launches.fetch_add(1);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                                 const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
+{
+    if (U <= 0) return cudaSuccess;
+    switch (family_chain_len(m.fam)) {
+    case 3: return node_eval_jvp_chains<3>(m, ee, wsign, U, q, qd, qdd, W, dtau_dq, dtau_dqd, s);
+    case 6: return node_eval_jvp_chains<6>(m, ee, wsign, U, q, qd, qdd, W, dtau_dq, dtau_dqd, s);
+    case 7: return node_eval_jvp_chains<7>(m, ee, wsign, U, q, qd, qdd, W, dtau_dq, dtau_dqd, s);
+    default: return launch_node_eval_jvp_dual(m, ee, wsign, U, q, qd, qdd, W, dtau_dq, dtau_dqd, s);
+    }
+}
+
 cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
                                double *M, cudaStream_t s)
 {
@@ -661,6 +773,9 @@ cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, cons
         break;
     case FAM_CHAIN6:
         k_fd_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, A, B, C);
+        break;
+    case FAM_FOREST12x6:
+        k_fd_derivs<12, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<12> *>(m.static_params), U, q, qd, tau, A, B, C);
         break;
     case FAM_CHAIN7:
         k_fd_derivs<7, 7><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, tau, A, B, C);
