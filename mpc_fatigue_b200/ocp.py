@@ -200,6 +200,36 @@ class ThermalMPCNodes:
         return {"tau": _aos(tau, (B, N)), "q_defect": _aos(qn, (B, N)) - q[:, 1:], "T_defect": Tn - Temp[:, 1:],
                 "T_violation": (Tn - self.temperature_bound).clamp_min(0.0).amax(dim=(1, 2))}
 
+    def box_rows(self, q, qd, F_L, F_R, mass: float, rel_pos0, rel_ori0, box_ini) -> dict:
+        """Rows of the dual-arm box-carrying OCP that involve both end-effectors (mpc_principal.py:229-260) and its running
+        cost (:281-284); needs exactly two end-effector frames (left, right).
+
+        q [B, N+1, n], qd [B, N, n], F_L / F_R [B, N, 3] world-frame forces the arms exert, rel_pos0 / rel_ori0 [B, 3]
+        (relative pose at the initial condition), box_ini [3].  Returns force_eq, moment_eq, rel_pos, rel_ori (each
+        [B, N, 3], residuals that the NLP pins to zero) and cost [B]."""
+        if len(self.frames) != 2:
+            raise ValueError("box rows need a left and a right end-effector frame")
+        B, N, n = qd.shape
+        qs = _soa(q[:, :N])
+        pL, RL = self.ev.fk(self.frames[0], qs)
+        pR, RR = self.ev.fk(self.frames[1], qs)
+        pL, pR = _aos(pL, (B, N)), _aos(pR, (B, N))
+        RL, RR = _aos(RL, (B, N)).reshape(B, N, 3, 3), _aos(RR, (B, N)).reshape(B, N, 3, 3)
+        Fdes = torch.tensor([0.0, 0.0, 9.81 * mass], dtype=torch.float64, device=q.device)  # :156
+        rel = torch.einsum("bnji,bnj->bni", RL, pR - pL)  # R01^T (pR - pL), :241
+        prev = torch.cat([torch.as_tensor(rel_pos0, dtype=torch.float64, device=q.device).reshape(B, 1, 3), rel[:, :-1]], dim=1)
+        Ro = RL @ RR.transpose(-1, -2)  # :248
+        sk = 0.5 * (Ro - Ro.transpose(-1, -2))
+        e = torch.stack([sk[..., 2, 1], sk[..., 2, 0], sk[..., 1, 0]], dim=-1)  # :252-255
+        pbox = 0.5 * (pL + pR)
+        dbox = pbox - torch.as_tensor(box_ini, dtype=torch.float64, device=q.device)
+        cost = (1000.0 * (dbox * dbox).sum(-1) + 100.0 * (qd * qd).sum(-1) + 10.0 * (F_L * F_L).sum(-1) + 10.0 * (F_R * F_R).sum(-1)).sum(-1)
+        return {"force_eq": F_L + F_R - Fdes,
+                "moment_eq": torch.linalg.cross(pL - pR, F_L) + torch.linalg.cross(pR - pL, F_R),
+                "rel_pos": rel - prev,
+                "rel_ori": e - torch.as_tensor(rel_ori0, dtype=torch.float64, device=q.device).reshape(B, 1, 3),
+                "cost": cost, "pL": pL, "pR": pR}
+
 
 def temp_simulation(Ic: float, Tin: float, T: float = 120.0, N: int = 200, Tbound: float = 70.0, ktau: float = 1.0):
     """Closed-form twin of python/Libraries/TemperatureModel.py:TempSimulation (constant current, zero speed):
