@@ -574,8 +574,10 @@ struct Dyn {
     // the columns of M (CRBA); M is factorised M = L D L^T in place.  For short chains (n <~ 9) this is cheaper than ABA
     // (no 6x6 articulated inertias to carry and transform).  Static forests of revolute chains only (parent = i - 1).
     // =========================================================================================
-    template <int L>
-    static MPCF_DI bool fd_crba(const MP &m, const T *q, const T *qd, const T *tau, T *qdd)
+    // MINV: also return C = M^-1 per chain as a packed lower triangle, Minv[chain * L (L + 1) / 2 + r (r + 1) / 2 + c], c <= r
+    // (from the factors: C = Lm^-T D^-1 Lm^-1) — the Jacobian pipeline's derivative kernel consumes it.
+    template <int L, bool MINV = false>
+    static MPCF_DI bool fd_crba(const MP &m, const T *q, const T *qd, const T *tau, T *qdd, T *Minv = nullptr)
     {
         static_assert(MP::kStatic, "fd_crba needs a compile-time forest of chains");
         constexpr int N = MAXN;
@@ -706,6 +708,28 @@ struct Dyn {
 #pragma unroll
                 for (int k = i + 1; k < L; ++k) x[i] -= Lm[k][i] * x[k];
                 qdd[c0 + i] = x[i];
+            }
+            if constexpr (MINV) {
+                T Li[L][L];  // Lm^-1 (unit lower triangular), strictly-lower entries
+#pragma unroll
+                for (int j = 0; j < L; ++j)
+#pragma unroll
+                    for (int i = j + 1; i < L; ++i) {
+                        T e = -Lm[i][j];
+#pragma unroll
+                        for (int k = j + 1; k < i; ++k) e -= Lm[i][k] * Li[k][j];
+                        Li[i][j] = e;
+                    }
+                T *Cp = Minv + (c0 / L) * (L * (L + 1) / 2);
+#pragma unroll
+                for (int i = 0; i < L; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        T e = (i == j) ? Dinv[i] : Li[i][j] * Dinv[i];  // k = i term: Li[i][i] = 1
+#pragma unroll
+                        for (int k = i + 1; k < L; ++k) e += (Li[k][i] * Dinv[k]) * Li[k][j];
+                        Cp[i * (i + 1) / 2 + j] = e;
+                    }
             }
         }
         return ok;

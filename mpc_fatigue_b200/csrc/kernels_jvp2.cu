@@ -64,8 +64,24 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
     for (int s = 0; s < 4; ++s) {
         const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
         const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
-        D::xdot(m, xs, t, k);
         double *w = ws + W::chunk(lu / 32, s) + W::kPlanes2 * 32 + (lu & 31);
+        if constexpr (N == L) {
+            // forward dynamics through M; C = M^-1 goes straight to the stage chunk (K2 reads it, K3 consumes it)
+            double Cs[N * (N + 1) / 2];
+            D::template fd_crba<L, true>(m, xs, xs + N, t, k + N, Cs);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                k[i] = xs[N + i];
+                k[2 * N + i] = D::fatigue_rhs(m, i, xs[2 * N + i], t[i], xs[N + i]);
+            }
+            double *c = ws + W::chunk(lu / 32, s) + 2 * N * N * 32 + (lu & 31);
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int cc = 0; cc < N; ++cc) __stcs(c + (r * N + cc) * 32, Cs[r >= cc ? r * (r + 1) / 2 + cc : cc * (cc + 1) / 2 + r]);
+        } else {
+            D::xdot(m, xs, t, k);
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             __stcs(w + i * 32, xs[i]);
@@ -91,8 +107,26 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ K2
+MPCF_DI void cp_async8(double *smem, const double *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// where k_stage_derivs finds C = M^-1 (lower triangle): its own column of the shared-memory slab, or the stage chunk
+struct CFromShared {
+    double *base;
+    int stride;
+    MPCF_DI void ready() const { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+    MPCF_DI double operator()(int r, int c) const { return base[(r * (r + 1) / 2 + c) * stride]; }
+};
+template <int N>
+struct CFromGlobal {
+    const double *o;
+    MPCF_DI void ready() const {}
+    MPCF_DI double operator()(int r, int c) const { return o[(2 * N * N + r * N + c) * 32]; }
+};
+
 template <int N, int L, bool KSMEM>
-__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws)
+__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws, int zero)
 {
     const StaticModel<N, L> m{P};
     using W = WsLayout<N>;
@@ -110,7 +144,26 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
     }
     // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
     auto emit = [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); };
-    if (KSMEM) {
+    if constexpr (N == L) {
+        // M^-1 of this stage was written by k_step_stages
+        if (KSMEM) {
+            // slab: (S, xi, eta) of links 0 .. N-2, then the lower triangle of C, copied asynchronously (no registers, its
+            // DRAM latency hides under the forward pass); every thread touches only its own column of the slab
+            extern __shared__ double k2_slab[];
+            SharedLinkStore ks{k2_slab + threadIdx.x, (int)blockDim.x};
+            CFromShared Cs{k2_slab + 18 * (N - 1) * blockDim.x + threadIdx.x, (int)blockDim.x};
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c <= r; ++c)
+                    cp_async8(Cs.base + (r * (r + 1) / 2 + c) * Cs.stride, o + (2 * N * N + r * N + c) * 32);
+            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks, zero);
+        } else {
+            LocalLinkStore<N> ks;
+            CFromGlobal<N> Cs{o};
+            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks, zero);
+        }
+    } else if (KSMEM) {
         extern __shared__ double k2_slab[];
         SharedLinkStore ks{k2_slab + threadIdx.x, (int)blockDim.x};
         FdDerivs<StaticModel<N, L>, L>::run_emit_ks(m, q, qd, qdd, emit, ks);
@@ -631,7 +684,7 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             if (N <= 6) {
-                e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * N * kThreads * (int)sizeof(double));
+                e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double));
                 if (e != cudaSuccess) return e;
             }
             attr_set[dev] = true;
@@ -647,10 +700,10 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
         if (k2smem && N <= 6) {  // (N = 7: 129 KB per block would leave one block per SM)  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
-            constexpr int slab = 18 * N * kThreads * (int)sizeof(double);
-            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
+            constexpr int slab = (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double);
+            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws, 0);
         } else {
-            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
+            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws, 0);
         }
         prof_end(s);
         prof_begin(2, s);
