@@ -67,6 +67,7 @@ static void fill_static(const HostModel &h, StaticParams<N> &p, int first = 0)
         std::memcpy(p.fat[i], &h.fat[4 * g], 4 * sizeof(double));
     }
     std::memcpy(p.grav, h.grav, sizeof p.grav);
+    p.fence0 = 0;
 }
 
 static bool is_forest(const HostModel &h, int L)

@@ -576,6 +576,7 @@ struct Dyn {
     // =========================================================================================
     // MINV: also return C = M^-1 per chain as a packed lower triangle, Minv[chain * L (L + 1) / 2 + r (r + 1) / 2 + c], c <= r
     // (from the factors: C = Lm^-T D^-1 Lm^-1) — the Jacobian pipeline's derivative kernel consumes it.
+    // (Per-link scheduling fences, StaticModel::skip, were tried here: fewer spills, but the RK4 step kernel ran 4 % slower.)
     template <int L, bool MINV = false>
     static MPCF_DI bool fd_crba(const MP &m, const T *q, const T *qd, const T *tau, T *qdd, T *Minv = nullptr)
     {

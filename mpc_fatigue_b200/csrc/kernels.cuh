@@ -14,6 +14,7 @@ namespace mpcf {
 template <int N>
 struct StaticParams {
     double Rp[N][9], pp[N][3], mass[N], mc[N][3], Io[N][6], arm[N], fat[N][4], grav[3];
+    int fence0;  // always 0; see StaticModel::skip
 };
 
 // ---- run-time topology: model blob staged into shared memory by every block ----

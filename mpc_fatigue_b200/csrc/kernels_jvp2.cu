@@ -126,7 +126,7 @@ struct CFromGlobal {
 };
 
 template <int N, int L, bool KSMEM>
-__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws, int zero)
+__global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws)
 {
     const StaticModel<N, L> m{P};
     using W = WsLayout<N>;
@@ -157,11 +157,11 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
 #pragma unroll
                 for (int c = 0; c <= r; ++c)
                     cp_async8(Cs.base + (r * (r + 1) / 2 + c) * Cs.stride, o + (2 * N * N + r * N + c) * 32);
-            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks, zero);
+            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
         } else {
             LocalLinkStore<N> ks;
             CFromGlobal<N> Cs{o};
-            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks, zero);
+            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
         }
     } else if (KSMEM) {
         extern __shared__ double k2_slab[];
@@ -211,9 +211,31 @@ __global__ void __launch_bounds__(kThreads) k_rnea_derivs(const __grid_constant_
 #pragma unroll
         for (int cc = 0; cc < N; ++cc)
             if (r / L != cc / L) { Dq[(size_t)(r * N + cc) * U + u] = 0.0; Dv[(size_t)(r * N + cc) * U + u] = 0.0; Mo[(size_t)(r * N + cc) * U + u] = 0.0; }
-    LocalLinkStore<N> ks;
-    auto emit = [&](int mat, int r, int cc, double v) { (mat == 0 ? Dq : (mat == 1 ? Dv : Mo))[(size_t)(r * N + cc) * U + u] = v; };
-    FdDerivs<StaticModel<N, L>, L>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
+    if constexpr (N == L) {
+        extern __shared__ double link_slab[];
+        SharedLinkStore ks{link_slab + threadIdx.x, (int)blockDim.x};
+        struct Hooks {
+            double *Dq, *Dv, *Mo;
+            long U, u;
+            MPCF_DI void link(int, const double *, const double *) const {}
+            MPCF_DI void pair(int k, int j, const LinkFwd &, const LinkFwd &, double dqkj, double dqjk, double dvkj, double dvjk, double mkj) const
+            {
+                Dq[(size_t)(k * N + j) * U + u] = dqkj;
+                Dv[(size_t)(k * N + j) * U + u] = dvkj;
+                Mo[(size_t)(k * N + j) * U + u] = mkj;
+                if (j < k) {
+                    Dq[(size_t)(j * N + k) * U + u] = dqjk;
+                    Dv[(size_t)(j * N + k) * U + u] = dvjk;
+                    Mo[(size_t)(j * N + k) * U + u] = mkj;
+                }
+            }
+        } hooks{Dq, Dv, Mo, U, u};
+        FdDerivs<StaticModel<N, L>, L>::run_id_stream(m, a, b, c, hooks, ks);
+    } else {
+        LocalLinkStore<N> ks;
+        auto emit = [&](int mat, int r, int cc, double v) { (mat == 0 ? Dq : (mat == 1 ? Dv : Mo))[(size_t)(r * N + cc) * U + u] = v; };
+        FdDerivs<StaticModel<N, L>, L>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
+    }
 }
 
 // Reference-mode torque rows tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e (force_optimization_pilz_6DOF.py:134,
@@ -221,7 +243,66 @@ __global__ void __launch_bounds__(kThreads) k_rnea_derivs(const __grid_constant_
 // ID part: the world-frame pairing pass of derivs.cuh.  External part: with S_i = [o_i x z_i ; z_i] and the wrench moved to the
 // world origin, Wo = [F ; n + p_f x F] (F, n fixed in world axes, p_f attached to the frame's link),
 //   J_e^T W |_i = S_i . Wo,    d/dq_j = [j < i] (S_j x S_i) . Wo + ang(S_i) . ((lin(S_j) + ang(S_j) x p_f) x F),   i, j on the path to e
-template <int N>
+template <int N, int NEE>
+struct NodeEvalJvpHooks {
+    static constexpr int NE = NEE > 0 ? NEE : 1;
+    // one serial chain = joints [c0, c0 + N) of an ntot-joint forest; wrench e acts on the frame carried by chain joint je[e]
+    // (-1: not on this chain) at the world point pf[e]; Wo[e] = [F ; n + pf x F] is the wrench moved to the world origin
+    double *Dq, *Dv;
+    long U, u;
+    int ntot, c0;
+    double wsign;
+    int je[NE];
+    double pl[NE][3], pf[NE][3], Wo[NE][6];
+    MPCF_DI void link(int i, const double *R, const double *o)
+    {
+#pragma unroll
+        for (int e = 0; e < NEE; ++e)
+            if (je[e] == i) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) pf[e][r] = o[r] + R[3 * r] * pl[e][0] + R[3 * r + 1] * pl[e][1] + R[3 * r + 2] * pl[e][2];
+                double t[3];
+                cross3(pf[e], Wo[e], t);  // Wo[3..5] held the moment n so far
+#pragma unroll
+                for (int r = 0; r < 3; ++r) Wo[e][3 + r] += t[r];
+            }
+    }
+    // h_j = (lin(S_j) + ang(S_j) x pf) x F
+    MPCF_DI void hvec(const LinkFwd &Kj, int e, double *h) const
+    {
+        double t[3], dp[3];
+        cross3(Kj.S + 3, pf[e], t);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dp[r] = Kj.S[r] + t[r];
+        cross3(dp, Wo[e], h);
+    }
+    MPCF_DI void pair(int k, int j, const LinkFwd &Kk, const LinkFwd &Kj, double dqkj, double dqjk, double dvkj, double dvjk, double) const
+    {
+#pragma unroll
+        for (int e = 0; e < NEE; ++e)
+            if (k <= je[e]) {  // both joints carry the frame (j <= k)
+                double hj[3];
+                hvec(Kj, e, hj);
+                double vkj = dot3(Kk.S + 3, hj);
+                if (j < k) {
+                    double x[6], hk[3];
+                    mxm(Kj.S, Kk.S, x);
+                    vkj += dot6(x, Wo[e]);
+                    hvec(Kk, e, hk);
+                    dqjk += wsign * dot3(Kj.S + 3, hk);
+                }
+                dqkj += wsign * vkj;
+            }
+        Dq[(size_t)((c0 + k) * ntot + c0 + j) * U + u] = dqkj;
+        Dv[(size_t)((c0 + k) * ntot + c0 + j) * U + u] = dvkj;
+        if (j < k) {
+            Dq[(size_t)((c0 + j) * ntot + c0 + k) * U + u] = dqjk;
+            Dv[(size_t)((c0 + j) * ntot + c0 + k) * U + u] = dvjk;
+        }
+    }
+};
+
+template <int N, int NEE>
 __global__ void __launch_bounds__(kThreads) k_node_eval_jvp(const __grid_constant__ StaticParams<N> P, long U, EeArgs ee, double wsign,
                                                            const double *q, const double *qd, const double *qdd, const double *W,
                                                            double *Dq, double *Dv, int ntot, int c0)
@@ -233,72 +314,26 @@ __global__ void __launch_bounds__(kThreads) k_node_eval_jvp(const __grid_constan
     double a[N], b[N], c[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
-    LocalLinkStore<N> ks;
-    double dq[N][N];
-    auto emit = [&](int mat, int r, int cc, double v) {
-        if (mat == 0) dq[r][cc] = v;
-        else if (mat == 1) Dv[(size_t)((c0 + r) * ntot + c0 + cc) * U + u] = v;
-    };
-    FdDerivs<StaticModel<N, N>, N>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
-    if (ee.nee > 0) {
-        double oR[N][9], op[N][3];
-        Dyn<double, StaticModel<N, N>>::fk_all(m, a, oR, op);
-#pragma unroll 1
-        for (int e = 0; e < ee.nee; ++e) {
-            const int je = ee.f[e].joint - c0;
-            if (ee.f[e].joint < 0 || je < 0 || je >= N) continue;  // frame fixed to the world or carried by another chain
-            double pf[3] = {0.0, 0.0, 0.0};
+    // NEE = number of wrenches the instantiation handles (ee.nee <= NEE; missing ones are inert)
+    NodeEvalJvpHooks<N, NEE> hooks;
+    hooks.Dq = Dq; hooks.Dv = Dv; hooks.U = U; hooks.u = u; hooks.ntot = ntot; hooks.c0 = c0; hooks.wsign = wsign;
 #pragma unroll
-            for (int i = 0; i < N; ++i)
-                if (i == je) {
+    for (int e = 0; e < NEE; ++e) {
+        const int j = e < ee.nee ? ee.f[e].joint - c0 : -1;
+        hooks.je[e] = (e < ee.nee && ee.f[e].joint >= 0 && j >= 0 && j < N) ? j : -1;  // world-fixed frames / other chains: no term
 #pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        pf[r] = op[i][r] + oR[i][3 * r] * ee.f[e].p[0] + oR[i][3 * r + 1] * ee.f[e].p[1] + oR[i][3 * r + 2] * ee.f[e].p[2];
-                }
-            double Wo[6], F[3];
+        for (int r = 0; r < 3; ++r) { hooks.pl[e][r] = ee.f[e].p[r]; hooks.pf[e][r] = 0.0; }
 #pragma unroll
-            for (int r = 0; r < 3; ++r) { F[r] = W[(long)(6 * e + r) * U + u]; Wo[r] = F[r]; }
-            cross3(pf, F, Wo + 3);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) Wo[3 + r] += W[(long)(6 * e + 3 + r) * U + u];
-            double hj[N][3];
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                LinkFwd Kj;
-                ks.get(j, Kj);
-                double t[3], dp[3];
-                cross3(Kj.S + 3, pf, t);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) dp[r] = Kj.S[r] + t[r];
-                cross3(dp, F, hj[j]);
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                LinkFwd Ki;
-                ks.get(i, Ki);
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double val = dot3(Ki.S + 3, hj[j]);
-                    if (j < i) {
-                        LinkFwd Kj;
-                        ks.get(j, Kj);
-                        double x[6];
-                        mxm(Kj.S, Ki.S, x);
-                        val += dot6(x, Wo);
-                    }
-                    if (i <= je && j <= je) dq[i][j] += wsign * val;
-                }
-            }
-        }
+        for (int r = 0; r < 6; ++r) hooks.Wo[e][r] = (hooks.je[e] >= 0) ? W[(long)(6 * e + r) * U + u] : 0.0;
     }
-#pragma unroll
-    for (int r = 0; r < N; ++r) {
-#pragma unroll
-        for (int cc = 0; cc < N; ++cc) Dq[(size_t)((c0 + r) * ntot + c0 + cc) * U + u] = dq[r][cc];
+    extern __shared__ double link_slab[];
+    SharedLinkStore ks{link_slab + threadIdx.x, (int)blockDim.x};
+    FdDerivs<StaticModel<N, N>, N>::run_id_stream(m, a, b, c, hooks, ks);
+#pragma unroll 1
+    for (int r = 0; r < N; ++r)
 #pragma unroll 1
         for (int cc = 0; cc < ntot; ++cc)  // entries between different chains are structurally zero
             if (cc < c0 || cc >= c0 + N) { Dq[(size_t)((c0 + r) * ntot + cc) * U + u] = 0.0; Dv[(size_t)((c0 + r) * ntot + cc) * U + u] = 0.0; }
-    }
 }
 
 // generic fallback: one dual-number RNEA sweep per seed direction (blockIdx.y in [0, 3n): q, qd, qdd seeds)
@@ -701,9 +736,9 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
         if (k2smem && N <= 6) {  // (N = 7: 129 KB per block would leave one block per SM)  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
             constexpr int slab = (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double);
-            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws, 0);
+            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
         } else {
-            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws, 0);
+            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
         }
         prof_end(s);
         prof_begin(2, s);
@@ -766,6 +801,9 @@ cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, co
     }
 }
 
+// shared-memory slab of the streaming derivative kernels: (S, xi, eta) of links 0 .. n-2, one column per thread
+static constexpr int link_slab_bytes(int n) { return 18 * (n - 1) * kThreads * (int)sizeof(double); }
+
 template <int L>
 static cudaError_t node_eval_jvp_chains(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                                         const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
@@ -774,8 +812,16 @@ static cudaError_t node_eval_jvp_chains(const LaunchModel &m, const EeArgs &ee, 
     const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params);
     for (int c = 0; c < m.n / L; ++c) {
         const size_t off = (size_t)c * L * U;
-        k_node_eval_jvp<L><<<gb, kThreads, 0, s>>>(cp[c], U, ee, wsign, q + off, qd + off, qdd ? qdd + off : nullptr, W, dtau_dq, dtau_dqd,
-                                                    m.n, c * L);
+        auto go = [&](auto kern) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(L));
+            if (e != cudaSuccess) return e;
+            kern<<<gb, kThreads, link_slab_bytes(L), s>>>(cp[c], U, ee, wsign, q + off, qd + off, qdd ? qdd + off : nullptr, W, dtau_dq, dtau_dqd,
+                                                         m.n, c * L);
+            return cudaSuccess;
+        };
+        const cudaError_t e = ee.nee == 0 ? go(k_node_eval_jvp<L, 0>) : ee.nee == 1 ? go(k_node_eval_jvp<L, 1>)
+                              : ee.nee == 2 ? go(k_node_eval_jvp<L, 2>) : go(k_node_eval_jvp<L, MPCF_MAX_EE>);
+        if (e != cudaSuccess) return e;
         g_launches.fetch_add(1);
     }
     return cudaGetLastError();
@@ -798,15 +844,22 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
 {
     if (U <= 0) return cudaSuccess;
     const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    cudaError_t e;
     switch (m.fam) {
     case FAM_CHAIN3:
-        k_rnea_derivs<3, 3><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        e = cudaFuncSetAttribute(k_rnea_derivs<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(3));
+        if (e != cudaSuccess) return e;
+        k_rnea_derivs<3, 3><<<gb, kThreads, link_slab_bytes(3), s>>>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
         break;
     case FAM_CHAIN6:
-        k_rnea_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        e = cudaFuncSetAttribute(k_rnea_derivs<6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(6));
+        if (e != cudaSuccess) return e;
+        k_rnea_derivs<6, 6><<<gb, kThreads, link_slab_bytes(6), s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
         break;
     case FAM_CHAIN7:
-        k_rnea_derivs<7, 7><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
+        e = cudaFuncSetAttribute(k_rnea_derivs<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(7));
+        if (e != cudaSuccess) return e;
+        k_rnea_derivs<7, 7><<<gb, kThreads, link_slab_bytes(7), s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
         break;
     default:
         return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);

@@ -37,6 +37,10 @@ struct StaticModel {
     MPCF_DI double arm(int i) const { return P.arm[i]; }
     MPCF_DI double fat(int i, int k) const { return P.fat[i][k]; }
     MPCF_DI double grav(int k) const { return P.grav[k]; }
+    // Scheduling fence for fully unrolled link loops: `if (m.skip(i)) continue;` is never taken (fence0 == 0) but the
+    // compiler cannot know, so every link's work stays in its own basic block and ptxas does not hoist later links' loads
+    // and arithmetic over earlier ones (which multiplies the live registers: k_stage_derivs' stack frame 2.7 KB -> 0.1 KB).
+    MPCF_DI bool skip(int i) const { return P.fence0 > i; }
 };
 
 template <int MAXN_>
@@ -58,6 +62,7 @@ struct GenericModel {
     MPCF_DI double arm(int i) const { return d[22 * n_ + i]; }
     MPCF_DI double fat(int i, int k) const { return d[23 * n_ + 4 * i + k]; }
     MPCF_DI double grav(int k) const { return d[27 * n_ + k]; }
+    MPCF_DI bool skip(int) const { return false; }
 };
 
 // ---------------------------------------------------------------------------------------------
