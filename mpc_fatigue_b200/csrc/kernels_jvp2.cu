@@ -704,22 +704,34 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
                             cudaStream_t s, int ntot = N, int c0 = 0)
 {
     using W = WsLayout<N>;
-    constexpr int NBUF = (N <= 6) ? ((6 * W::kStageBytes + 256 <= 227 * 1024) ? 6 : 4) : 0;
+    // chain-rule kernel: bulk-copy ring as deep as 227 KB of shared memory allows; 3 N + 1 column warps of 96 registers fit
+    // the register file up to N = 6, longer chains run two columns per thread
+    constexpr bool kTma = N <= 7;
+    constexpr int kRingMax = (227 * 1024 - 256) / (int)W::kStageBytes;
+    constexpr int NBUF = kTma ? (kRingMax > 6 ? 6 : kRingMax) : 0;
+    constexpr int kCpwDefault = (3 * N + 1 <= 19) ? 1 : 2;
     constexpr size_t smem = (size_t)NBUF * W::kStageBytes + 2 * NBUF * sizeof(unsigned long long);
-    if constexpr (N <= 6) {
+    // derivative kernel: 2 blocks per SM with the link slab in shared memory
+    constexpr int kK2Threads = (2 * (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double) <= 227 * 1024) ? kThreads : 96;
+    constexpr int kK2Slab = (18 * (N - 1) + N * (N + 1) / 2) * kK2Threads * (int)sizeof(double);
+    constexpr bool kK2Smem = N == L && 2 * kK2Slab <= 227 * 1024;
+    if constexpr (kTma) {
         static bool attr_set[64] = {};  // function attributes are per device: set them once on each device a process uses
         const int dev = current_device();
         if (!attr_set[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
+            cudaError_t e = cudaSuccess;
+            if constexpr (kCpwDefault == 1) {
+                e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            if (N <= 6) {
-                e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double));
+            if constexpr (kK2Smem) {
+                e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2Slab);
                 if (e != cudaSuccess) return e;
             }
             attr_set[dev] = true;
@@ -734,21 +746,27 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         prof_end(s);
         prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
-        if (k2smem && N <= 6) {  // (N = 7: 129 KB per block would leave one block per SM)  // per-link (S, xi, eta) in shared memory: 18 N doubles per thread (110 KB per block for N = 6)
-            constexpr int slab = (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double);
-            k_stage_derivs<N, L, true><<<dim3(gb, 4), kThreads, slab, s>>>(P, cnt, ws);
-        } else {
-            k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
+        bool k2done = false;
+        if constexpr (kK2Smem) {
+            if (k2smem) {
+                k_stage_derivs<N, L, true><<<dim3((unsigned)((cnt + kK2Threads - 1) / kK2Threads), 4), kK2Threads, kK2Slab, s>>>(P, cnt, ws);
+                k2done = true;
+            }
         }
+        if (!k2done) k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
         prof_end(s);
         prof_begin(2, s);
-        if constexpr (N <= 6) {
+        if constexpr (kTma) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
             static const int cpw_env = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
-            const int cpw = (3 * N + 1 > 19) ? 2 : cpw_env;  // more than 19 columns: two per thread (register file)
-            if (cpw == 2) (ntot == N ? k_chain_rule_tma<N, L, NBUF, 2, true> : k_chain_rule_tma<N, L, NBUF, 2, false>)<<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
-            else if (ntot == N) k_chain_rule_tma<N, L, NBUF, 1, true><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
-            else k_chain_rule_tma<N, L, NBUF, 1, false><<<g3, 32 * (3 * N + 1), smem, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            const int cpw = kCpwDefault == 2 ? 2 : cpw_env;
+            if (cpw == 2) {
+                (ntot == N ? k_chain_rule_tma<N, L, NBUF, 2, true> : k_chain_rule_tma<N, L, NBUF, 2, false>)<<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(
+                    P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            } else if constexpr (kCpwDefault == 1) {
+                (ntot == N ? k_chain_rule_tma<N, L, NBUF, 1, true> : k_chain_rule_tma<N, L, NBUF, 1, false>)<<<g3, 32 * (3 * N + 1), smem, s>>>(
+                    P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            }
         } else {
             k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
         }
