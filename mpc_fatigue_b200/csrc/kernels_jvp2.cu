@@ -392,8 +392,16 @@ struct ColumnState {
     double Xq[N], Xv[N], Xf[N], aq[N], av[N], af[N];
     int jq, jv, jt;
     bool isdt;
-    double tauj;
+    double ktau;  // tau columns: d(fatigue rhs_jt)/d tau_jt = 2 kappa c_tau tau_jt (one scalar: the column's own joint)
+    double xq1;  // the single non-zero of X_2[q] (stage index 1) for q and qd columns
 
+    MPCF_DI void set_tau(const StaticParams<N> &P, double tauj)
+    {
+        ktau = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (i == jt) ktau = 2.0 * P.fat[i][1] * P.fat[i][2] * tauj;
+    }
     MPCF_DI void init(int col)
     {
         jq = col < N ? col : -1;
@@ -407,6 +415,7 @@ struct ColumnState {
             Xf[i] = 0.0;
             aq[i] = Xq[i]; av[i] = Xv[i]; af[i] = 0.0;
         }
+        xq1 = 0.0;
     }
     // second half of a stage: fatigue rows, accumulators, next stage state
     MPCF_DI void finish(const StaticParams<N> &P, int s, const double *w1, double h, const double *nv)
@@ -417,7 +426,7 @@ struct ColumnState {
         for (int i = 0; i < N; ++i) {
             const double qds = w1[(N + i) * 32];
             double kf = 2.0 * P.fat[i][1] * P.fat[i][3] * qds * Xv[i] - P.fat[i][0] * Xf[i];
-            if (i == jt) kf += 2.0 * P.fat[i][1] * P.fat[i][2] * tauj;
+            if (i == jt) kf += ktau;
             double yq = h * Xv[i], yf = h * kf, yv = h * nv[i];
             if (isdt) {
                 yq += qds;
@@ -430,28 +439,54 @@ struct ColumnState {
             Xq[i] = ((i == jq) ? 1.0 : 0.0) + cs * yq;
             Xv[i] = ((i == jv) ? 1.0 : 0.0) + cs * yv;
             Xf[i] = cs * yf;
+            if (s == 0 && (i == jq || i == jv)) xq1 = Xq[i];
         }
     }
     // one RK4 stage for ONE column; w points at this lane's element of plane 0 of the (tile, stage) chunk
     MPCF_DI void stage(const StaticParams<N> &P, int s, const double *w, double h)
     {
+        // the three cases are separate straight-line blocks (one branch per stage, not per row): the scheduler batches the
+        // shared-memory loads of a whole block, which is what hides their latency at 19 warps per SM
         double nv[N];
+        if (s == 0) {  // X_1 is a unit vector (or zero): the product is a single entry of A_1 / B_1
 #pragma unroll
-        for (int r = 0; r < N; ++r) {
-            double kv = 0.0;
-            if (s == 0) {  // X_1 is a unit vector (or zero): the product is a single entry of A_1 / B_1
+            for (int r = 0; r < N; ++r) {
+                double kv = 0.0;
                 if (jq >= 0 && jq / L == r / L) kv = w[(r * N + jq) * 32];
                 if (jv >= 0 && jv / L == r / L) kv = w[(N * N + r * N + jv) * 32];
-            } else {
+                nv[r] = kv;
+            }
+        } else if (s == 1 && !isdt) {
+            // X_2[q] = X_1[q] + (dt/2) X_1[qd] still has a single non-zero (q and qd columns) or none (tau columns)
+            const int js = jq >= 0 ? jq : jv;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                double kv = 0.0;
+                if (js >= 0 && js / L == r / L) kv = w[(r * N + js) * 32] * xq1;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    if (r / L != c / L) continue;
+                    kv = fma(w[(N * N + r * N + c) * 32], Xv[c], kv);
+                }
+                nv[r] = kv;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                double kv = 0.0;
 #pragma unroll
                 for (int c = 0; c < N; ++c) {
                     if (r / L != c / L) continue;
                     kv = fma(w[(r * N + c) * 32], Xq[c], kv);
                     kv = fma(w[(N * N + r * N + c) * 32], Xv[c], kv);
                 }
+                nv[r] = kv;
             }
-            if (jt >= 0 && jt / L == r / L) kv += w[(2 * N * N + r * N + jt) * 32];
-            nv[r] = kv;
+        }
+        if (jt >= 0) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+                if (jt / L == r / L) nv[r] += w[(2 * N * N + r * N + jt) * 32];
         }
         finish(P, s, w + 3 * N * N * 32, h, nv);
     }
@@ -598,10 +633,10 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
         const double h = dt_u ? dt_u[u] : dt;
         ColumnState<N, L> a, b;
         a.init(col0);
-        a.tauj = a.jt >= 0 ? tau[(size_t)a.jt * U + u] : 0.0;
+        a.set_tau(P, a.jt >= 0 ? tau[(size_t)a.jt * U + u] : 0.0);
         if (CPW == 2) {
             b.init(two ? col1 : col0);
-            b.tauj = b.jt >= 0 ? tau[(size_t)b.jt * U + u] : 0.0;
+            b.set_tau(P, b.jt >= 0 ? tau[(size_t)b.jt * U + u] : 0.0);
         }
 #pragma unroll 1
         for (int s = 0; s < 4; ++s, ++it) {
@@ -637,7 +672,7 @@ __global__ void __launch_bounds__(32 * NCY, 2)
     for (int col = threadIdx.y; col < NC; col += blockDim.y) {
         ColumnState<N, L> st;
         st.init(col);
-        st.tauj = st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0;
+        st.set_tau(P, st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0);
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) st.stage(P, s, ws + W::chunk(blockIdx.x, s) + threadIdx.x, h);
         st.template store<false>(P, col, h, U, u, jac, ntot, c0);
