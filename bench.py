@@ -31,7 +31,7 @@ DT = 2.0 / N_NODES
 ARMATURE = 1e-2
 NDOF = 6
 # DRAM bytes per unit of the Jacobian pipeline from the committed ncu --set full capture (profiles/); None = not captured
-TRAFFIC_BYTES_PER_UNIT = 17400  # (1.11 + 8.92 + 8.21) GB per 2^20 units, profiles/r01_jvp_pipeline.md
+TRAFFIC_BYTES_PER_UNIT = 13546  # (2.32 + 3.67 + 8.21) GB per 2^20 units, profiles/r01_jvp_pipeline.md
 
 
 # ---- frozen work model (BASELINE.md §3 / SURVEY.md §8d) ----
