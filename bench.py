@@ -206,6 +206,10 @@ def run_gpu(args) -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from mpc_fatigue_b200.dist import bind_to_gpu_numa_node
+    # multi-GPU: every rank's pinned staging buffers on the NUMA node of its own GPU (N = 1 keeps all host cores, which
+    # the cpu_baseline leg uses)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("MPCF_NUMA_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -329,7 +333,7 @@ def run_gpu(args) -> None:
             "dtype": "f64", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(stats["d2h_bytes"]), "steps": e2e_steps,
+                    "d2h_bytes_per_step": int(stats["d2h_bytes"]), "steps": e2e_steps, "numa_node_rank0": numa,
                     "what": "HostStepPipeline.run: pinned host q,qd,tau,f -> chunked H2D -> step_rk4_jvp + cost_residual -> "
                             "D2H of q+,qd+,f+, the 348 structurally non-zero Jacobian planes (of 450: d(q+,qd+)/df = 0, df+/df "
                             "diagonal) and per-scenario cost/residuals into pinned host staging (PCIe-bound: 2.9 KB per unit)"},

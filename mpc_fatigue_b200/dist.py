@@ -6,6 +6,8 @@ per-scenario (cost, residual) rows, which the reduction kernel writes directly i
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -39,3 +41,35 @@ def allgather_rows(local: torch.Tensor, counts: list[int] | None = None, group=N
     if all(c == Bmax for c in counts):
         return recv.permute(1, 0, 2).reshape(R, world * Bmax)
     return torch.cat([recv[r, :, : counts[r]] for r in range(world)], dim=1)
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> int | None:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that the pinned staging buffers it
+    allocates afterwards (first touch) and the copy-engine traffic into them stay on that node.  One process per GPU:
+    without this the ranks of a multi-GPU run share whatever node the launcher left them on.
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = _parse_cpulist(fh.read()) & set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, AttributeError, ValueError):
+        return None
