@@ -1,9 +1,11 @@
 // kernels_jvp2.cu — analytic Jacobian pipeline of the RK4 dynamics+fatigue step for static chain families
-// (chain3 / chain6 / forest12x6).  Three kernels per chunk of units, staged through a caller-provided
-// workspace (all planes SoA `[row][chunk]`, coalesced):
+// (chain3 / chain6 / chain7; forests of two such chains run the pipeline once per chain).  Three kernels per chunk of
+// units, staged through a caller-provided workspace (all planes SoA `[row][chunk]`, coalesced):
 //
-//   K1 step_stages   thread = unit            primal RK4 (ABA) -> x+, and per stage (q_s, qd_s, qdd_s, fdot_s) -> workspace
-//   K2 stage_derivs  thread = (unit, stage)   A_s = dqdd/dq, B_s = dqdd/dqd, C_s = M^-1 (derivs.cuh)        -> workspace
+//   K1 step_stages   thread = unit            primal RK4 (forward dynamics through M = L D L^T) -> x+, and per stage
+//                                             (q_s, qd_s, qdd_s, fdot_s) and C_s = M^-1                      -> workspace
+//   K2 stage_derivs  thread = (unit, stage)   A_s = dqdd/dq = -C dID/dq, B_s = dqdd/dqd = -C dID/dqd, column by column as
+//                                             the backward pass completes them (derivs.cuh: run_cols)        -> workspace
 //   K3 chain_rule    warp = (32 units, column) forward accumulation of d x+/d (q, qd, tau, dt) through the four stages.
 //                    Persistent CTAs; one producer thread streams each (tile, stage) chunk of the workspace into a
 //                    shared-memory ring with cp.async.bulk (TMA) + mbarriers; consumer warps read A_s/B_s/C_s from
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
                                                          double dt, const double *dt_u, double *qn, double *qdn, double *fn,
                                                          double *ws)
 {
+    static_assert(N == L, "the pipeline runs one serial chain at a time (forests: one launch per chain)");
     const StaticModel<N, L> m{P};
     using D = Dyn<double, StaticModel<N, L>>;
     using W = WsLayout<N>;
@@ -65,8 +68,7 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
         const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
         const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
         double *w = ws + W::chunk(lu / 32, s) + W::kPlanes2 * 32 + (lu & 31);
-        if constexpr (N == L) {
-            // forward dynamics through M; C = M^-1 goes straight to the stage chunk (K2 reads it, K3 consumes it)
+        {   // forward dynamics through M; C = M^-1 goes straight to the stage chunk (K2 reads it, K3 consumes it)
             double Cs[N * (N + 1) / 2];
             D::template fd_crba<L, true>(m, xs, xs + N, t, k + N, Cs);
 #pragma unroll
@@ -79,8 +81,6 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
             for (int r = 0; r < N; ++r)
 #pragma unroll
                 for (int cc = 0; cc < N; ++cc) __stcs(c + (r * N + cc) * 32, Cs[r >= cc ? r * (r + 1) / 2 + cc : cc * (cc + 1) / 2 + r]);
-        } else {
-            D::xdot(m, xs, t, k);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -144,31 +144,22 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
     }
     // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
     auto emit = [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); };
-    if constexpr (N == L) {
-        // M^-1 of this stage was written by k_step_stages
-        if (KSMEM) {
-            // slab: (S, xi, eta) of links 0 .. N-2, then the lower triangle of C, copied asynchronously (no registers, its
-            // DRAM latency hides under the forward pass); every thread touches only its own column of the slab
-            extern __shared__ double k2_slab[];
-            SharedLinkStore ks{k2_slab + threadIdx.x, (int)blockDim.x};
-            CFromShared Cs{k2_slab + 18 * (N - 1) * blockDim.x + threadIdx.x, (int)blockDim.x};
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-#pragma unroll
-                for (int c = 0; c <= r; ++c)
-                    cp_async8(Cs.base + (r * (r + 1) / 2 + c) * Cs.stride, o + (2 * N * N + r * N + c) * 32);
-            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
-        } else {
-            LocalLinkStore<N> ks;
-            CFromGlobal<N> Cs{o};
-            FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
-        }
-    } else if (KSMEM) {
+    // M^-1 of this stage was written by k_step_stages
+    if (KSMEM) {
+        // slab: (S, xi, eta) of links 0 .. N-2, then the lower triangle of C, copied asynchronously (no registers, its
+        // DRAM latency hides under the forward pass); every thread touches only its own column of the slab
         extern __shared__ double k2_slab[];
         SharedLinkStore ks{k2_slab + threadIdx.x, (int)blockDim.x};
-        FdDerivs<StaticModel<N, L>, L>::run_emit_ks(m, q, qd, qdd, emit, ks);
+        CFromShared Cs{k2_slab + 18 * (N - 1) * blockDim.x + threadIdx.x, (int)blockDim.x};
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c <= r; ++c) cp_async8(Cs.base + (r * (r + 1) / 2 + c) * Cs.stride, o + (2 * N * N + r * N + c) * 32);
+        FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
     } else {
-        FdDerivs<StaticModel<N, L>, L>::run_emit(m, q, qd, qdd, emit);
+        LocalLinkStore<N> ks;
+        CFromGlobal<N> Cs{o};
+        FdDerivs<StaticModel<N, L>, L>::run_cols(m, q, qd, qdd, Cs, emit, ks);
     }
 }
 
