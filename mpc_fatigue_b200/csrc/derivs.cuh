@@ -42,6 +42,10 @@ MPCF_DI void mxf(const double *a, const double *f, double *o)
     cross3(a, f, t1);
     o[3] = t0[0] + t1[0]; o[4] = t0[1] + t1[1]; o[5] = t0[2] + t1[2];
 }
+// one out-of-line copy of sincos (its large-argument slow path is ~150 instructions per inlined call site; the derivative
+// kernels are instruction-fetch bound at 110 KB of straight-line code)
+__device__ __noinline__ void sincos_shared(double x, double *s, double *c) { sincos(x, s, c); }
+
 MPCF_DI double dot6(const double *a, const double *b)
 {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
@@ -462,7 +466,7 @@ struct FdDerivs {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             if (m.skip(i)) continue;
-            sincos(q[i], &sn[i], &cs[i]);
+            sincos_shared(q[i], &sn[i], &cs[i]);
             LinkFwd Ki;
             link_kin(m, i, cs[i], sn[i], qd[i], qdd[i], R, o, v, a, Ki);
             if (i == N - 1) Klast = Ki;  // the backward pass starts at this link: no round trip through the store
