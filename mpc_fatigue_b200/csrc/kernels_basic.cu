@@ -271,10 +271,149 @@ cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const do
 {
     return dispatch<JacBody>(m, U, 1, s, f, q, J);
 }
+// world pose of link i of a serial chain from its parent's (R, o) and the joint's (cos, sin); i == 0 starts the chain
+template <class MP>
+MPCF_DI void chain_link_pose(const MP &m, int i, double c, double s, double *R, double *o)
+{
+    double Rl[9], Rn[9], on[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Rl[3 * r + 0] = m.Rp(i, 3 * r) * c + m.Rp(i, 3 * r + 1) * s;
+        Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * c - m.Rp(i, 3 * r) * s;
+        Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
+    }
+    if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rn[k] = Rl[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) on[k] = m.pp(i, k);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) Rn[3 * r + cc] = R[3 * r] * Rl[cc] + R[3 * r + 1] * Rl[3 + cc] + R[3 * r + 2] * Rl[6 + cc];
+            on[r] = o[r] + R[3 * r] * m.pp(i, 0) + R[3 * r + 1] * m.pp(i, 1) + R[3 * r + 2] * m.pp(i, 2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = on[k];
+}
+
+// Reference-mode node for ONE serial chain of a static family (joints [c0, c0 + N) of the model; the pointers already address
+// the chain's planes): tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e, q+ = q + h qd, thermal ZOH.  The frame kinematics run
+// as a register-resident world-frame chain after the local-frame RNEA (same sin/cos), twice: the first sweep finds the frame
+// points p_f, the second forms S_i = [o_i x z_i ; z_i] link by link and adds S_i . Wo with the wrench moved to the world
+// origin, Wo = [F ; n + p_f x F], for every joint up to the frame's — no per-link pose arrays, no run-time indexing.
+// NEE = number of wrenches handled (ee.nee <= NEE).
+template <int N, int NEE>
+__global__ void __launch_bounds__(kThreads, 3) node_eval_chain_kernel(const __grid_constant__ StaticParams<N> P, long U, EeArgs ee, double wsign,
+                                                                     const double *q, const double *qd, const double *qdd, const double *W,
+                                                                     const double *T, double h, ZohArg zoh, double *tau, double *qnext,
+                                                                     double *Tnext, int c0)
+{
+    const StaticModel<N, N> m{P};
+    using D = Dyn<double, StaticModel<N, N>>;
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double a[N], b[N], c[N], t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        a[i] = q[i * U + u];
+        b[i] = qd ? qd[i * U + u] : 0.0;
+        c[i] = qdd ? qdd[i * U + u] : 0.0;
+    }
+    JointVar<double> jv[N];
+    D::template rnea_impl<false>(m, a, jv, b, c, t);  // fills jv on the way
+    if constexpr (NEE > 0) {
+        if (m.skip(0)) return;  // never taken (StaticModel::skip): the dynamics and the frame kinematics stay in separate blocks
+        int je[NEE];
+        double Wo[NEE][6];
+#pragma unroll
+        for (int e = 0; e < NEE; ++e) {
+            const int j = e < ee.nee ? ee.f[e].joint - c0 : -1;
+            je[e] = (e < ee.nee && ee.f[e].joint >= 0 && j >= 0 && j < N) ? j : -1;  // world-fixed frame / other chain: no term
+#pragma unroll
+            for (int r = 0; r < 6; ++r) Wo[e][r] = je[e] >= 0 ? W[(long)(6 * e + r) * U + u] : 0.0;
+        }
+        double R[9], o[3];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            chain_link_pose(m, i, jv[i].c, jv[i].s, R, o);
+#pragma unroll
+            for (int e = 0; e < NEE; ++e)
+                if (je[e] == i) {
+                    double pf[3], mo[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        pf[r] = o[r] + R[3 * r] * ee.f[e].p[0] + R[3 * r + 1] * ee.f[e].p[1] + R[3 * r + 2] * ee.f[e].p[2];
+                    cross3(pf, Wo[e], mo);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) Wo[e][3 + r] += mo[r];
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            chain_link_pose(m, i, jv[i].c, jv[i].s, R, o);
+            const double z[3] = {R[2], R[5], R[8]};
+            double S[3];
+            cross3(o, z, S);
+#pragma unroll
+            for (int e = 0; e < NEE; ++e) {
+                const double acc = S[0] * Wo[e][0] + S[1] * Wo[e][1] + S[2] * Wo[e][2] + z[0] * Wo[e][3] + z[1] * Wo[e][4] + z[2] * Wo[e][5];
+                if (i <= je[e]) t[i] += wsign * acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        tau[i * U + u] = t[i];
+        if (qnext) qnext[i * U + u] = a[i] + h * b[i];
+        if (Tnext) {
+            const double Pl = m.fat(i, 2) * t[i] * t[i] + m.fat(i, 3) * b[i] * b[i];
+            const double Ti = T[i * U + u];
+            const double lam = m.fat(i, 0), za = zoh.a[c0 + i];
+            Tnext[i * U + u] = (lam == 0.0) ? Ti + h * m.fat(i, 1) * Pl : za * Ti + (1.0 - za) * (m.fat(i, 1) / lam) * Pl;
+        }
+    }
+}
+
+template <int L>
+static cudaError_t node_eval_chains(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
+                                    const double *qdd, const double *W, const double *T, double h, const ZohArg &zoh, double *tau,
+                                    double *qnext, double *Tnext, cudaStream_t s)
+{
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params);
+    for (int c = 0; c < m.n / L; ++c) {
+        const size_t off = (size_t)c * L * U;
+        auto at = [off](auto *p) { return p ? p + off : p; };
+        auto go = [&](auto kern) {
+            kern<<<gb, kThreads, 0, s>>>(cp[c], U, ee, wsign, q + off, at(qd), at(qdd), W, at(T), h, zoh, tau + off, at(qnext), at(Tnext), c * L);
+        };
+        if (ee.nee == 0) go(node_eval_chain_kernel<L, 0>);
+        else if (ee.nee == 1) go(node_eval_chain_kernel<L, 1>);
+        else if (ee.nee == 2) go(node_eval_chain_kernel<L, 2>);
+        else go(node_eval_chain_kernel<L, MPCF_MAX_EE>);
+        g_launches.fetch_add(1);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                              const double *qdd, const double *W, const double *T, double h, const ZohArg &zoh, double *tau,
                              double *qnext, double *Tnext, bool jtw_only, cudaStream_t s)
 {
+    if (U <= 0) return cudaSuccess;
+    if (!jtw_only) {
+        switch (family_chain_len(m.fam)) {
+        case 3: return node_eval_chains<3>(m, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, s);
+        case 6: return node_eval_chains<6>(m, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, s);
+        case 7: return node_eval_chains<7>(m, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, s);
+        default: break;
+        }
+    }
     return dispatch<NodeEvalBody>(m, U, 1, s, ee, wsign, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, jtw_only);
 }
 cudaError_t launch_node_eval_jvp_dual(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
