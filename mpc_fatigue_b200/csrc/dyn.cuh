@@ -193,8 +193,20 @@ struct Dyn {
     {
         rnea_impl<true>(m, nullptr, const_cast<JointVar<T> *>(jv), qd, qdd, tau);
     }
+    // Ext: external link forces.  ext.link(m, i, jv_i, f_i) is called once per link in the forward sweep, after the link's
+    // net force f_i = I a + v x* I v (link coordinates, [force ; moment about the joint origin]) is formed; whatever it adds
+    // to f_i is carried to the joints by the backward sweep like any other force (tau = ID - J^T f_ext).
+    struct NoExt {
+        MPCF_DI void link(const MP &, int, const JointVar<T> &, T *) {}
+    };
     template <bool HAVE_JV>
     static MPCF_DI void rnea_impl(const MP &m, const T *q, JointVar<T> *jv, const T *qd, const T *qdd, T *tau)
+    {
+        NoExt none;
+        rnea_impl<HAVE_JV>(m, q, jv, qd, qdd, tau, none);
+    }
+    template <bool HAVE_JV, class Ext>
+    static MPCF_DI void rnea_impl(const MP &m, const T *q, JointVar<T> *jv, const T *qd, const T *qdd, T *tau, Ext &ext)
     {
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
@@ -226,6 +238,7 @@ struct Dyn {
             crossf(v[i], h, fb);
 #pragma unroll
             for (int k = 0; k < 6; ++k) f[i][k] = fa[k] + fb[k];
+            ext.link(m, i, jv[i], f[i]);
         }
 #pragma unroll UNR
         for (int i = n - 1; i >= 0; --i) {

@@ -271,42 +271,55 @@ cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const do
 {
     return dispatch<JacBody>(m, U, 1, s, f, q, J);
 }
-// world pose of link i of a serial chain from its parent's (R, o) and the joint's (cos, sin); i == 0 starts the chain
-template <class MP>
-MPCF_DI void chain_link_pose(const MP &m, int i, double c, double s, double *R, double *o)
-{
-    double Rl[9], Rn[9], on[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        Rl[3 * r + 0] = m.Rp(i, 3 * r) * c + m.Rp(i, 3 * r + 1) * s;
-        Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * c - m.Rp(i, 3 * r) * s;
-        Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
-    }
-    if (i == 0) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Rn[k] = Rl[k];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) on[k] = m.pp(i, k);
-    } else {
+// Contact wrenches as external link forces of the RNEA (serial chain): W_e = [F ; n] is given in world axes at the frame
+// point carried by chain joint je[e] (LOCAL_WORLD_ALIGNED, bridge.hpp:144), so in the coordinates of that link it is
+// [R^T F ; R^T n + p x R^T F] with R the link's world orientation and p the frame's offset in the link — only the rotation
+// chain is needed, and it advances inside the RNEA's own forward sweep.  tau = ID + wsign * sum_e J_e^T W_e.
+template <int N, int NEE>
+struct WrenchExt {
+    double R[9];  // world orientation of the link the sweep is at
+    int je[NEE > 0 ? NEE : 1];
+    double Wl[NEE > 0 ? NEE : 1][6], pl[NEE > 0 ? NEE : 1][3];
+    double wsign;
+    MPCF_DI void link(const StaticModel<N, N> &m, int i, const JointVar<double> &jv, double *f)
+    {
+        if (NEE == 0) return;
+        double Rl[9], Rn[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) Rn[3 * r + cc] = R[3 * r] * Rl[cc] + R[3 * r + 1] * Rl[3 + cc] + R[3 * r + 2] * Rl[6 + cc];
-            on[r] = o[r] + R[3 * r] * m.pp(i, 0) + R[3 * r + 1] * m.pp(i, 1) + R[3 * r + 2] * m.pp(i, 2);
+            Rl[3 * r + 0] = m.Rp(i, 3 * r) * jv.c + m.Rp(i, 3 * r + 1) * jv.s;
+            Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * jv.c - m.Rp(i, 3 * r) * jv.s;
+            Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
         }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                Rn[3 * r + c] = (i == 0) ? Rl[3 * r + c] : R[3 * r] * Rl[c] + R[3 * r + 1] * Rl[3 + c] + R[3 * r + 2] * Rl[6 + c];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+        for (int e = 0; e < NEE; ++e)
+            if (je[e] == i) {
+                double Fl[3], nl[3], t[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    Fl[c] = R[c] * Wl[e][0] + R[3 + c] * Wl[e][1] + R[6 + c] * Wl[e][2];
+                    nl[c] = R[c] * Wl[e][3] + R[3 + c] * Wl[e][4] + R[6 + c] * Wl[e][5];
+                }
+                cross3(pl[e], Fl, t);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    f[c] += wsign * Fl[c];
+                    f[3 + c] += wsign * (nl[c] + t[c]);
+                }
+            }
     }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) o[k] = on[k];
-}
+};
 
 // Reference-mode node for ONE serial chain of a static family (joints [c0, c0 + N) of the model; the pointers already address
-// the chain's planes): tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e, q+ = q + h qd, thermal ZOH.  The frame kinematics run
-// as a register-resident world-frame chain after the local-frame RNEA (same sin/cos), twice: the first sweep finds the frame
-// points p_f, the second forms S_i = [o_i x z_i ; z_i] link by link and adds S_i . Wo with the wrench moved to the world
-// origin, Wo = [F ; n + p_f x F], for every joint up to the frame's — no per-link pose arrays, no run-time indexing.
-// NEE = number of wrenches handled (ee.nee <= NEE).
+// the chain's planes): tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e, q+ = q + h qd, thermal ZOH — one RNEA sweep pair with
+// the wrenches injected as external link forces (WrenchExt).  NEE = number of wrenches handled (ee.nee <= NEE).
 template <int N, int NEE>
 __global__ void __launch_bounds__(kThreads, 3) node_eval_chain_kernel(const __grid_constant__ StaticParams<N> P, long U, EeArgs ee, double wsign,
                                                                      const double *q, const double *qd, const double *qdd, const double *W,
@@ -324,48 +337,19 @@ __global__ void __launch_bounds__(kThreads, 3) node_eval_chain_kernel(const __gr
         b[i] = qd ? qd[i * U + u] : 0.0;
         c[i] = qdd ? qdd[i * U + u] : 0.0;
     }
-    JointVar<double> jv[N];
-    D::template rnea_impl<false>(m, a, jv, b, c, t);  // fills jv on the way
-    if constexpr (NEE > 0) {
-        if (m.skip(0)) return;  // never taken (StaticModel::skip): the dynamics and the frame kinematics stay in separate blocks
-        int je[NEE];
-        double Wo[NEE][6];
+    WrenchExt<N, NEE> ext;
+    ext.wsign = wsign;
 #pragma unroll
-        for (int e = 0; e < NEE; ++e) {
-            const int j = e < ee.nee ? ee.f[e].joint - c0 : -1;
-            je[e] = (e < ee.nee && ee.f[e].joint >= 0 && j >= 0 && j < N) ? j : -1;  // world-fixed frame / other chain: no term
+    for (int e = 0; e < NEE; ++e) {
+        const int j = e < ee.nee ? ee.f[e].joint - c0 : -1;
+        ext.je[e] = (e < ee.nee && ee.f[e].joint >= 0 && j >= 0 && j < N) ? j : -1;  // world-fixed frame / other chain: no term
 #pragma unroll
-            for (int r = 0; r < 6; ++r) Wo[e][r] = je[e] >= 0 ? W[(long)(6 * e + r) * U + u] : 0.0;
-        }
-        double R[9], o[3];
+        for (int r = 0; r < 6; ++r) ext.Wl[e][r] = ext.je[e] >= 0 ? W[(long)(6 * e + r) * U + u] : 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            chain_link_pose(m, i, jv[i].c, jv[i].s, R, o);
-#pragma unroll
-            for (int e = 0; e < NEE; ++e)
-                if (je[e] == i) {
-                    double pf[3], mo[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        pf[r] = o[r] + R[3 * r] * ee.f[e].p[0] + R[3 * r + 1] * ee.f[e].p[1] + R[3 * r + 2] * ee.f[e].p[2];
-                    cross3(pf, Wo[e], mo);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) Wo[e][3 + r] += mo[r];
-                }
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            chain_link_pose(m, i, jv[i].c, jv[i].s, R, o);
-            const double z[3] = {R[2], R[5], R[8]};
-            double S[3];
-            cross3(o, z, S);
-#pragma unroll
-            for (int e = 0; e < NEE; ++e) {
-                const double acc = S[0] * Wo[e][0] + S[1] * Wo[e][1] + S[2] * Wo[e][2] + z[0] * Wo[e][3] + z[1] * Wo[e][4] + z[2] * Wo[e][5];
-                if (i <= je[e]) t[i] += wsign * acc;
-            }
-        }
+        for (int r = 0; r < 3; ++r) ext.pl[e][r] = ee.f[e].p[r];
     }
+    JointVar<double> jv[N];
+    D::template rnea_impl<false>(m, a, jv, b, c, t, ext);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         tau[i * U + u] = t[i];
