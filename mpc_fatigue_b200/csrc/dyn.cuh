@@ -770,25 +770,28 @@ struct Dyn {
         return ok;
     }
 
-    // classical RK4, tau held over the step
+    // classical RK4, tau held over the step.  The four stages run as a rolled loop: fully unrolled, the step kernel of a
+    // 6-joint chain is 190 KB of straight-line code and spends half its time waiting for instruction fetch
+    // (profiles/r01_jvp_pipeline.md); rolled, one stage body (48 KB) stays in the instruction cache.
     static MPCF_DI bool step_rk4(const MP &m, const T *x, const T *tau, T dt, T *xn)
     {
         const int n3 = 3 * m.n();
         constexpr int UNR3 = MP::kStatic ? 3 * MAXN : 1;
         T k[3 * MAXN], xs[3 * MAXN];
-        bool ok = xdot(m, x, tau, k);
-        const T hdt = 0.5 * dt, dt6 = dt * (1.0 / 6.0), dt3 = dt * (1.0 / 3.0);
 #pragma unroll UNR3
-        for (int i = 0; i < n3; ++i) { xn[i] = x[i] + dt6 * k[i]; xs[i] = x[i] + hdt * k[i]; }
-        ok &= xdot(m, xs, tau, k);
+        for (int i = 0; i < n3; ++i) { xn[i] = x[i]; xs[i] = x[i]; }
+        bool ok = true;
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+            ok &= xdot(m, xs, tau, k);
+            const T w = dt * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+            const T c = dt * (s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0));
 #pragma unroll UNR3
-        for (int i = 0; i < n3; ++i) { xn[i] += dt3 * k[i]; xs[i] = x[i] + hdt * k[i]; }
-        ok &= xdot(m, xs, tau, k);
-#pragma unroll UNR3
-        for (int i = 0; i < n3; ++i) { xn[i] += dt3 * k[i]; xs[i] = x[i] + dt * k[i]; }
-        ok &= xdot(m, xs, tau, k);
-#pragma unroll UNR3
-        for (int i = 0; i < n3; ++i) xn[i] += dt6 * k[i];
+            for (int i = 0; i < n3; ++i) {
+                xn[i] += w * k[i];
+                xs[i] = x[i] + c * k[i];
+            }
+        }
         return ok;
     }
 };
