@@ -71,5 +71,5 @@ def bind_to_gpu_numa_node(device_index: int) -> int | None:
             return None
         os.sched_setaffinity(0, cpus)
         return node
-    except (OSError, AttributeError, ValueError):
+    except (OSError, AttributeError, ValueError, RuntimeError, AssertionError):  # no sysfs entry / no driver / old torch
         return None

@@ -218,6 +218,35 @@ def test_step_rk4_jvp(setup, direct):
     assert np.all(off == 0.0)
 
 
+@pytest.mark.parametrize("urdf", ["pilz6", "pilz6x2"])
+def test_step_rk4_jvp_fast_motion(urdf):
+    """The derivative kernel rebuilds each link's velocity / acceleration from its child's by undoing the joint; joint
+    speeds 8x the URDF limit, 4x the usual torques and a long step stress the cancellation in that recursion."""
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import Model, data_urdf
+    from oracle.pyoracle import Oracle
+    from oracle.urdf_model import load_urdf
+    xml = data_urdf(urdf)
+    m, om = Model.from_urdf(xml, armature=1e-2), load_urdf(xml, armature=1e-2)
+    ev, orc = BatchEvaluator(m), Oracle(om)
+    U, dt = 130, 0.05
+    q, qd, tau, f, _ = random_inputs(om, U, seed=77)
+    qd, tau = np.ascontiguousarray(8.0 * qd), np.ascontiguousarray(4.0 * tau)
+    rq, rqd, rf, rj = orc.step_rk4_jvp(q, qd, tau, f, dt)
+    d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f)]
+    gq, gqd, gf, gj = ev.step_rk4_jvp(*d, dt)
+    n = m.n
+    assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
+    gj = gj.cpu().numpy()
+    for r0, r1 in ((0, n), (n, 2 * n), (2 * n, 3 * n)):
+        assert rel_err(gj[r0:r1], rj[r0:r1]) < TOL, (r0, rel_err(gj[r0:r1], rj[r0:r1]))
+    Dq, Dv, M = ev.rnea_derivs(d[0], d[1])
+    rDq, rDv, rM = orc.rnea_derivs(q, qd, None)
+    for got, ref in ((Dq, rDq), (Dv, rDv), (M, rM)):
+        assert rel_err(got.cpu().numpy(), ref) < TOL
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases of the batch axis and of the workspace pipeline
 # ---------------------------------------------------------------------------------------------

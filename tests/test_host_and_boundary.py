@@ -174,6 +174,14 @@ def test_synth_batches_are_shard_invariant_and_in_range():
     assert not torch.equal(q, synth_batch(lim, 0, B, N, seed=99, device="cpu")[0])
 
 
+def test_numa_binding_helpers():
+    from mpc_fatigue_b200.dist import _parse_cpulist, bind_to_gpu_numa_node
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and _parse_cpulist("") == set()
+    if not torch.cuda.is_available():
+        before = os.sched_getaffinity(0)
+        assert bind_to_gpu_numa_node(0) is None and os.sched_getaffinity(0) == before  # no topology: nothing changes
+
+
 def test_shard_range_partitions():
     for B, W in ((10, 3), (8, 8), (1048576, 8), (5, 8)):
         spans = [shard_range(B, r, W) for r in range(W)]
