@@ -320,6 +320,27 @@ def run_gpu(args) -> None:
         e2e_s = float(tt.item())
     e2e_value = world * U * e2e_steps / e2e_s
 
+    # same host-facing call, but only the per-scenario cost / residual rows return to the host (states and Jacobians stay
+    # on the device): the variant for a device-resident consumer; reported beside `e2e`, never instead of it
+    pipe_r = HostStepPipeline(model, dev, chunk_units=1 << 19, outputs="reduced")
+    pipe_r.run(hq, hqd, htau, hf, DT, B, N)
+    fence()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        stats_r = pipe_r.run(hq, hqd, htau, hf, DT, B, N)
+        if world > 1:
+            allgather_rows(pipe_r.reduced)
+    fence()
+    e2e_r_s = time.perf_counter() - w0
+    if world > 1:
+        tt = torch.tensor([e2e_r_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_r_s = float(tt.item())
+    e2e_reduced = {"value": world * U * e2e_steps / e2e_r_s, "unit": UNIT, "h2d_bytes_per_step": int(stats_r["h2d_bytes"]),
+                   "d2h_bytes_per_step": int(stats_r["d2h_bytes"]),
+                   "what": "HostStepPipeline(outputs='reduced'): pinned host inputs -> H2D -> step_rk4_jvp + cost_residual -> D2H of the "
+                           "[4, B] per-scenario cost/residual rows only"}
+
     if rank == 0:
         fm = flop_model(n)
         peaks = measured_peaks()
@@ -337,6 +358,7 @@ def run_gpu(args) -> None:
                     "what": "HostStepPipeline.run: pinned host q,qd,tau,f -> chunked H2D -> step_rk4_jvp + cost_residual -> "
                             "D2H of q+,qd+,f+, the 348 structurally non-zero Jacobian planes (of 450: d(q+,qd+)/df = 0, df+/df "
                             "diagonal) and per-scenario cost/residuals into pinned host staging (PCIe-bound: 2.9 KB per unit)"},
+            "e2e_reduced_rows": e2e_reduced,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": best_tf, "unit": "TFLOP/s", "frac": ach_tf / best_tf,
                          "traffic": TRAFFIC_BYTES_PER_UNIT * U if TRAFFIC_BYTES_PER_UNIT else None,
                          "traffic_source": "profiles/r01_jvp_pipeline.md: dram read+write of the 3 kernels per unit x U (ncu --set full)",

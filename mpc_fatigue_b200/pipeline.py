@@ -20,7 +20,14 @@ from .model import Model
 
 
 class HostStepPipeline:
-    def __init__(self, model: Model, device, chunk_units: int = 1 << 19, with_jacobian: bool = True, skip_structural_zeros: bool = False):
+    def __init__(self, model: Model, device, chunk_units: int = 1 << 19, with_jacobian: bool = True, skip_structural_zeros: bool = False,
+                 outputs: str = "all"):
+        """outputs = "all": states + Jacobian planes + per-scenario rows come back to the host (what a host-side NLP solver needs).
+        outputs = "reduced": only the per-scenario (cost, defect, torque-bound, fatigue-bound) rows come back; states and
+        Jacobians are computed but stay on the device (what the multi-GPU path gathers)."""
+        if outputs not in ("all", "reduced"):
+            raise ValueError("outputs must be 'all' or 'reduced'")
+        self.outputs = outputs
         self.model, self.dev = model, torch.device(device)
         self.ev = BatchEvaluator(model, self.dev)
         self.chunk_units = int(chunk_units)
@@ -133,16 +140,17 @@ class HostStepPipeline:
                 ev_cmp[slot].record(self.s_cmp)
                 # ---- D2H of the chunk's outputs (contiguous) ----
                 self.s_out.wait_event(ev_cmp[slot])
-                if consume is not None and len(pending) == 2:  # the slot about to be overwritten goes to the consumer first
-                    hand_over(pending.pop(0))
-                with torch.cuda.stream(self.s_out):
-                    hflat, dflat = self.h_out[slot].reshape(-1), d_out.reshape(-1)
-                    for dp, hr, cnt in self.segments:  # one DMA per contiguous run of planes
-                        hflat[hr * uc:(hr + cnt) * uc].copy_(dflat[dp * uc:(dp + cnt) * uc], non_blocking=True)
-                d2h += hrows * uc * 8
+                if self.outputs == "all":
+                    if consume is not None and len(pending) == 2:  # the slot about to be overwritten goes to the consumer first
+                        hand_over(pending.pop(0))
+                    with torch.cuda.stream(self.s_out):
+                        hflat, dflat = self.h_out[slot].reshape(-1), d_out.reshape(-1)
+                        for dp, hr, cnt in self.segments:  # one DMA per contiguous run of planes
+                            hflat[hr * uc:(hr + cnt) * uc].copy_(dflat[dp * uc:(dp + cnt) * uc], non_blocking=True)
+                    d2h += hrows * uc * 8
                 ev_out[slot] = torch.cuda.Event()
                 ev_out[slot].record(self.s_out)
-                if consume is not None:
+                if consume is not None and self.outputs == "all":
                     pending.append((slot, b0, b1, ev_out[slot]))
             for item in pending:
                 hand_over(item)

@@ -196,6 +196,13 @@ def test_host_pipeline_matches_direct_calls(torch_mod):
         assert torch.equal(v, full[sel][:, :, b0:b1])
     dropped = sorted(set(range(468)) - set(pz.plane_map))
     assert len(dropped) == 102 and float(full[torch.tensor(dropped)].abs().max()) == 0.0
+    # outputs="reduced": same computation, only the per-scenario rows come back
+    pr = HostStepPipeline(m, "cuda:0", chunk_units=N * 256, outputs="reduced")
+    st3 = pr.run(*host, dt, B, N)
+    assert st3["d2h_bytes"] == 4 * B * 8 and st3["h2d_bytes"] == stats["h2d_bytes"]
+    assert torch.equal(pr.h_red, red.cpu())
+    with pytest.raises(ValueError):
+        HostStepPipeline(m, "cuda:0", outputs="none")
 
 
 def test_full_size_properties(torch_mod):
