@@ -85,7 +85,8 @@ const char *mpcf_frame_name(const mpcf_model *model, int frame);
 long mpcf_model_export(const mpcf_model *model, const char *field, void *out, size_t cap_bytes);
 int mpcf_model_set_armature(mpcf_model *model, const double *arm /* [n] host */);
 int mpcf_model_set_fatigue(mpcf_model *model, const double *rows /* [n][4] host: lambda kappa ctau cv */);
-/* name of the kernel family a model dispatches to: "chain6", "forest12x6", "generic", ... */
+/* name of the kernel family a model dispatches to: "chain3", "chain6", "chain7", "forest12x6", "forest14x7" (compile-time
+ * topologies: serial revolute chains and forests of two of them) or "generic16" / "generic64" (run-time topology) */
 const char *mpcf_model_kernel_family(const mpcf_model *model);
 
 /* tau[n][U] = RNEA(q, qd, qdd); qdd may be NULL (= 0, as every reference caller passes) */
@@ -131,7 +132,7 @@ int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double 
 int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,
                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                             double *qdn, double *fn, double *jac, void *stream);
-/* Faster Jacobian path for serial-chain models ("chain3", "chain6", "forest12x6"): analytic forward-dynamics
+/* Faster Jacobian path for the compile-time families ("chain3", "chain6", "chain7", "forest12x6", "forest14x7"): analytic forward-dynamics
    derivatives per RK4 stage + a chain rule through the stages, staged through a caller-owned DEVICE workspace.
    mpcf_step_rk4_jvp_workspace_bytes() returns the size to allocate (bounded: units are processed in chunks),
    or 0 when the model has no workspace path.  With workspace == NULL (or too small, or such a model) the call
