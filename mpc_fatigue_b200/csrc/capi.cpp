@@ -278,6 +278,10 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
         d.insert(d.end(), h.grav, h.grav + 3);
         std::vector<int> ii(h.parent);
         ii.insert(ii.end(), h.jtype.begin(), h.jtype.end());
+        std::vector<int> keep(n, 0);  // link i's (v, a) are needed after link i + 1 has been visited
+        for (int j = 0; j < n; ++j)
+            if (h.parent[j] >= 0 && h.parent[j] != j - 1) keep[h.parent[j]] = 1;
+        ii.insert(ii.end(), keep.begin(), keep.end());
         cudaError_t e;
         if (!m->d_dbl && (e = cudaMalloc(&m->d_dbl, d.size() * sizeof(double))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");
         if (!m->d_int && (e = cudaMalloc(&m->d_int, ii.size() * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");

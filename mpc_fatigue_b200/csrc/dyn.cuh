@@ -208,6 +208,10 @@ struct Dyn {
     template <bool HAVE_JV, class Ext>
     static MPCF_DI void rnea_impl(const MP &m, const T *q, JointVar<T> *jv, const T *qd, const T *qdd, T *tau, Ext &ext)
     {
+        if constexpr (!MP::kStatic) {
+            rnea_tree<HAVE_JV>(m, q, jv, qd, qdd, tau, ext);
+            return;
+        }
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
         T v[MAXN][6], a[MAXN][6], f[MAXN][6];
@@ -249,6 +253,81 @@ struct Dyn {
                 force_to_parent(m, i, jv[i], f[i], fp);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) f[par][k] += fp[k];
+            }
+        }
+    }
+
+    // Run-time trees: the per-link arrays live in local memory (run-time indexing), and at 37 joints the sweeps are bound by
+    // that traffic, not by arithmetic.  Links are numbered so that most parents are i - 1: the sweep keeps the current
+    // link's (v, a) in registers, reads the arrays only when the parent is not the previous link and writes them only for
+    // links some later link branches off (m.keep); the backward sweep likewise carries the force of link i in registers into
+    // its parent when that is the next link visited.  Per chain-like link that leaves 6 doubles written and 6 read instead
+    // of 18 written and 30 read.
+    template <bool HAVE_JV, class Ext>
+    static MPCF_DI void rnea_tree(const MP &m, const T *q, JointVar<T> *jv, const T *qd, const T *qdd, T *tau, Ext &ext)
+    {
+        const int n = m.n();
+        T v[MAXN][6], a[MAXN][6], f[MAXN][6];
+        T vc[6], ac[6];
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            if (!HAVE_JV) joint_var(m, i, q[i], jv[i]);
+            const int par = m.parent(i), s = sidx(m, i);
+            T vp[6], ap[6];
+            if (par < 0) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { vp[k] = T(0.0); ap[k] = T(0.0); }
+                ap[0] = T(-m.grav(0)); ap[1] = T(-m.grav(1)); ap[2] = T(-m.grav(2));
+            } else if (par == i - 1) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { vp[k] = vc[k]; ap[k] = ac[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { vp[k] = v[par][k]; ap[k] = a[par][k]; }
+            }
+            motion_to_child(m, i, jv[i], vp, vc);
+            vc[s] += qd[i];
+            motion_to_child(m, i, jv[i], ap, ac);
+            T c[6];
+            bias_c(m, i, vc, qd[i], c);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ac[k] += c[k];
+            ac[s] += qdd[i];
+            if (m.keep(i)) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { v[i][k] = vc[k]; a[i][k] = ac[k]; }
+            }
+            T h[6], fa[6], fb[6], fi[6];
+            inertia_mul(m, i, vc, h);
+            inertia_mul(m, i, ac, fa);
+            crossf(vc, h, fb);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) fi[k] = fa[k] + fb[k];
+            ext.link(m, i, jv[i], fi);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) f[i][k] = fi[k];
+        }
+        T carry[6];  // force handed from link i + 1 to its parent i, when that is the link visited next
+        bool have = false;
+#pragma unroll 1
+        for (int i = n - 1; i >= 0; --i) {
+            const int par = m.parent(i), s = sidx(m, i);
+            T fi[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) fi[k] = f[i][k] + (have ? carry[k] : T(0.0));
+            tau[i] = fi[s] + m.arm(i) * qdd[i];
+            have = false;
+            if (par >= 0) {
+                T fp[6];
+                force_to_parent(m, i, jv[i], fi, fp);
+                if (par == i - 1) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) carry[k] = fp[k];
+                    have = true;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) f[par][k] += fp[k];
+                }
             }
         }
     }

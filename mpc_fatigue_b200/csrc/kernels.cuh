@@ -19,14 +19,15 @@ struct StaticParams {
 
 // ---- run-time topology: model blob staged into shared memory by every block ----
 // blob layout (doubles): Rp 9n | pp 3n | mass n | mc 3n | Io 6n | arm n | fat 4n | grav 3
-// followed by ints: parent n | jtype n
+// followed by ints: parent n | jtype n | keep n  (keep[i] = 1 when some link other than i + 1 has parent i, i.e. link i's
+// kinematic state must outlive the next link of the sweep)
 struct GenericBlob {
     const double *dbl;  // device
     const int *ints;    // device
     int n;
 };
 inline size_t blob_doubles(int n) { return (size_t)27 * n + 3; }
-inline size_t blob_smem_bytes(int n) { return blob_doubles(n) * sizeof(double) + (size_t)2 * n * sizeof(int); }
+inline size_t blob_smem_bytes(int n) { return blob_doubles(n) * sizeof(double) + (size_t)3 * n * sizeof(int); }
 
 struct FrameArg {
     int joint;  // parent joint, -1 = world

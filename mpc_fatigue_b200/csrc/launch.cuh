@@ -29,6 +29,7 @@ struct StaticModel {
     MPCF_DI int n() const { return N; }
     MPCF_DI int parent(int i) const { return (i % L == 0) ? -1 : i - 1; }
     MPCF_DI bool prismatic(int) const { return false; }
+    MPCF_DI bool keep(int) const { return true; }
     MPCF_DI double Rp(int i, int k) const { return P.Rp[i][k]; }
     MPCF_DI double pp(int i, int k) const { return P.pp[i][k]; }
     MPCF_DI double mass(int i) const { return P.mass[i]; }
@@ -54,6 +55,7 @@ struct GenericModel {
     MPCF_DI int n() const { return n_; }
     MPCF_DI int parent(int i) const { return ii[i]; }
     MPCF_DI bool prismatic(int i) const { return ii[n_ + i] != 0; }
+    MPCF_DI bool keep(int i) const { return ii[2 * n_ + i] != 0; }
     MPCF_DI double Rp(int i, int k) const { return d[9 * i + k]; }
     MPCF_DI double pp(int i, int k) const { return d[9 * n_ + 3 * i + k]; }
     MPCF_DI double mass(int i) const { return d[12 * n_ + i]; }
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericBlob blob, lon
     const int nd = 27 * n + 3;
     int *si = reinterpret_cast<int *>(smem + nd);
     for (int k = threadIdx.x; k < nd; k += blockDim.x) smem[k] = blob.dbl[k];
-    for (int k = threadIdx.x; k < 2 * n; k += blockDim.x) si[k] = blob.ints[k];
+    for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) si[k] = blob.ints[k];
     __syncthreads();
     const GenericModel<MAXN> m{n, smem, si};
     const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -26,7 +26,7 @@ def timed(fn, reps=3):
 
 for name, m, B, N, dt in (("C3 pilz6x2 (forest12x6)", Model.from_urdf(data_urdf("pilz6x2"), armature=1e-2), 8192, 100, 0.02),
                           ("Centauro-like dual arm 2x7 (forest14x7)", Model.synthetic("dual_arm", 14, seed=3, armature=1e-2), 8192, 40, 0.5 / 40),
-                          ("C4 humanoid37 (generic64)", Model.synthetic("humanoid", 37, seed=7, armature=1e-2), 1024, 40, 0.5 / 40)):
+                          ("C4 humanoid37 (generic64)", Model.synthetic("humanoid", 37, seed=7, armature=1e-2), 8192, 40, 0.5 / 40)):
     ev = BatchEvaluator(m)
     lim = {k: m.export(k) for k in ("q_lo", "q_hi", "v_max", "tau_max")}
     q, qd, tau, f = synth_batch(lim, 0, B, N, device="cuda")
@@ -38,7 +38,7 @@ for name, m, B, N, dt in (("C3 pilz6x2 (forest12x6)", Model.from_urdf(data_urdf(
     print("%s  U=%d  node_eval %8.3f ms  %.3e units/s" % (name, U, ms, U / ms * 1e3))
     ms = timed(lambda: ev.step_rk4(q, qd, tau, f, dt))
     print("%s  U=%d  step      %8.3f ms  %.3e units/s" % (name, U, ms, U / ms * 1e3))
-    Uj = U if m.kernel_family.startswith(("chain", "forest")) else U // 8
+    Uj = U if m.kernel_family.startswith(("chain", "forest")) else 5120
     sl = [t[:, :Uj].contiguous() for t in (q, qd, tau, f)]
     ms = timed(lambda: ev.step_rk4_jvp(*sl, dt), reps=2)
     print("%s  U=%d  step+jac  %8.3f ms  %.3e units/s" % (name, Uj, ms, Uj / ms * 1e3))
