@@ -513,6 +513,7 @@ struct Dyn {
     // Returns false when some D_i == 0 (singular without armature).
     static MPCF_DI bool aba(const MP &m, const T *q, const T *qd, const T *tau, T *qdd)
     {
+        if constexpr (!MP::kStatic) return aba_tree(m, q, qd, tau, qdd);
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
         AbaLink L[MAXN];
@@ -648,6 +649,204 @@ struct Dyn {
             a[s] += qa;
 #pragma unroll
             for (int k = 0; k < 6; ++k) pA[i][k] = a[k];
+        }
+        return ok;
+    }
+
+    // ABA for run-time trees.  Same arithmetic as aba(); what changes is where the per-link data live (cf. rnea_tree): the
+    // articulated inertia and bias force a link hands to its parent travel in registers when the parent is the link
+    // visited next (par == i - 1), the accumulator arrays IA / pA are touched only by links whose parent is elsewhere and
+    // are initialised only for links that have such children (m.keep), and the outward acceleration sweep keeps the
+    // current link's acceleration in registers.  Local-memory traffic per chain-like link drops from ~160 to ~45 doubles.
+    static MPCF_DI bool aba_tree(const MP &m, const T *q, const T *qd, const T *tau, T *qdd)
+    {
+        const int n = m.n();
+        AbaLink L[MAXN];
+        Art IA[MAXN];
+        T pA[MAXN][6];
+        bool ok = true;
+        {
+            T vc[6];
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                const int par = m.parent(i), s = sidx(m, i);
+                JointVar<T> jv;
+                joint_var(m, i, q[i], jv);
+                L[i].jv = jv;
+                T vp[6];
+                if (par < 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) vp[k] = T(0.0);
+                } else if (par == i - 1) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) vp[k] = vc[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) vp[k] = L[par].v[k];
+                }
+                if (par >= 0) motion_to_child(m, i, jv, vp, vc);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) vc[k] = T(0.0);
+                }
+                vc[s] += qd[i];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) L[i].v[k] = vc[k];
+                if (m.keep(i)) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { IA[i].A[k] = T(0.0); IA[i].C[k] = T(0.0); pA[i][k] = T(0.0); }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) IA[i].B[k] = T(0.0);
+                }
+            }
+        }
+        {
+            Art cI;    // what link i + 1 hands to link i
+            T cp[6];
+            bool have = false;
+#pragma unroll 1
+            for (int i = n - 1; i >= 0; --i) {
+                const int par = m.parent(i);
+                const bool pr = m.prismatic(i);
+                Art I;
+                T p[6], v[6];
+                if (m.keep(i)) {
+                    I = IA[i];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) p[k] = pA[i][k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { I.A[k] = T(0.0); I.C[k] = T(0.0); p[k] = T(0.0); }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) I.B[k] = T(0.0);
+                }
+                if (have) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { I.A[k] += cI.A[k]; I.C[k] += cI.C[k]; p[k] += cp[k]; }
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) I.B[k] += cI.B[k];
+                }
+                have = false;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) v[k] = L[i].v[k];
+                {
+                    const double ms = m.mass(i), cx = m.mc(i, 0), cy = m.mc(i, 1), cz = m.mc(i, 2);
+                    I.A[0] += ms; I.A[3] += ms; I.A[5] += ms;
+                    I.B[1] += cz;  I.B[2] += -cy;
+                    I.B[3] += -cz; I.B[5] += cx;
+                    I.B[6] += cy;  I.B[7] += -cx;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) I.C[k] += m.Io(i, k);
+                    T h[6], pb[6];
+                    inertia_mul(m, i, v, h);
+                    crossf(v, h, pb);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) p[k] += pb[k];
+                }
+                T U[6], D;
+                if (!pr) {
+                    U[0] = I.B[2]; U[1] = I.B[5]; U[2] = I.B[8];
+                    U[3] = I.C[2]; U[4] = I.C[4]; U[5] = I.C[5];
+                    D = I.C[5] + m.arm(i);
+                } else {
+                    U[0] = I.A[2]; U[1] = I.A[4]; U[2] = I.A[5];
+                    U[3] = I.B[6]; U[4] = I.B[7]; U[5] = I.B[8];
+                    D = I.A[5] + m.arm(i);
+                }
+                if (value_of(D) == 0.0) { ok = false; D = T(1.0); }
+                const T Dinv = recip(D);
+                const T u = tau[i] - p[pr ? 2 : 5];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) L[i].U[k] = U[k];
+                L[i].Dinv = Dinv;
+                L[i].u = u;
+                if (par >= 0) {
+                    T UD[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) UD[k] = U[k] * Dinv;
+                    const int rr[6] = {0, 0, 0, 1, 1, 2}, cc[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        I.A[k] -= UD[rr[k]] * U[cc[k]];
+                        I.C[k] -= UD[3 + rr[k]] * U[3 + cc[k]];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) I.B[3 * r + c] -= UD[r] * U[3 + c];
+                    T cb[6], pa[6];
+                    bias_c(m, i, v, qd[i], cb);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        pa[r] = p[r] + UD[r] * u + symget(I.A, r, 0) * cb[0] + symget(I.A, r, 1) * cb[1] + symget(I.A, r, 2) * cb[2] +
+                                I.B[3 * r] * cb[3] + I.B[3 * r + 1] * cb[4] + I.B[3 * r + 2] * cb[5];
+                        pa[3 + r] = p[3 + r] + UD[3 + r] * u + I.B[r] * cb[0] + I.B[3 + r] * cb[1] + I.B[6 + r] * cb[2] +
+                                    symget(I.C, r, 0) * cb[3] + symget(I.C, r, 1) * cb[4] + symget(I.C, r, 2) * cb[5];
+                    }
+                    const JointVar<T> jv = L[i].jv;
+                    if (!pr) {
+                        T c2 = jv.c * jv.c - jv.s * jv.s, s2 = 2.0 * (jv.c * jv.s);
+                        rotz_sym(I.A, jv.c, jv.s, c2, s2);
+                        rotz_sym(I.C, jv.c, jv.s, c2, s2);
+                        rotz_full(I.B, jv.c, jv.s);
+                    } else {
+                        T pz[3] = {T(0.0), T(0.0), jv.c};
+                        translate(I.A, I.B, I.C, pz);
+                    }
+                    Art O;
+                    rot_sym(m, i, I.A, O.A);
+                    rot_sym(m, i, I.C, O.C);
+                    rot_full(m, i, I.B, O.B);
+                    double pp[3] = {m.pp(i, 0), m.pp(i, 1), m.pp(i, 2)};
+                    translate(O.A, O.B, O.C, pp);
+                    T fp[6];
+                    force_to_parent(m, i, jv, pa, fp);
+                    if (par == i - 1) {
+                        cI = O;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) cp[k] = fp[k];
+                        have = true;
+                    } else {
+                        Art &Ip = IA[par];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) { Ip.A[k] += O.A[k]; Ip.C[k] += O.C[k]; pA[par][k] += fp[k]; }
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) Ip.B[k] += O.B[k];
+                    }
+                }
+            }
+        }
+        {
+            T ac[6];  // acceleration of the previous link; pA[i] is reused to hold a_i of the links others branch off
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                const int par = m.parent(i), s = sidx(m, i);
+                T ap[6], a[6], cb[6];
+                if (par < 0) {
+                    ap[0] = T(-m.grav(0)); ap[1] = T(-m.grav(1)); ap[2] = T(-m.grav(2));
+                    ap[3] = T(0.0); ap[4] = T(0.0); ap[5] = T(0.0);
+                } else if (par == i - 1) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) ap[k] = ac[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) ap[k] = pA[par][k];
+                }
+                motion_to_child(m, i, L[i].jv, ap, a);
+                bias_c(m, i, L[i].v, qd[i], cb);
+                T acc = L[i].u;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { a[k] += cb[k]; acc -= L[i].U[k] * a[k]; }
+                const T qa = L[i].Dinv * acc;
+                qdd[i] = qa;
+                a[s] += qa;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ac[k] = a[k];
+                if (m.keep(i)) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) pA[i][k] = a[k];
+                }
+            }
         }
         return ok;
     }
