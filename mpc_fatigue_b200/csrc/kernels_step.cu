@@ -4,6 +4,7 @@
 namespace mpcf {
 
 struct AbaBody {
+    static constexpr int kGenericMinBlocks = 3;
     template <class MP>
     static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, double *qdd)
     {
@@ -23,6 +24,7 @@ struct AbaBody {
 };
 
 struct StepBody {
+    static constexpr int kGenericMinBlocks = 3;
     template <class MP>
     static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, const double *f,
                             double dt, const double *dt_u, double *qn, double *qdn, double *fn)
@@ -51,6 +53,7 @@ struct StepBody {
 // Sequential rollout (single shooting): thread = scenario, the state (q, qd, f) stays in registers across the N steps;
 // tau is read per step (node-major planes, unit k*B + b) and the trajectory x_1..x_N is written in the same layout.
 struct RolloutBody {
+    static constexpr int kGenericMinBlocks = 3;
     template <class MP>
     static MPCF_DI void run(const MP &m, long b, long B, int N, const double *q0, const double *qd0, const double *f0, const double *tau,
                             double dt, double *qt, double *qdt, double *ft)
