@@ -263,12 +263,210 @@ cudaError_t launch_rnea(const LaunchModel &m, long U, const double *q, const dou
 {
     return dispatch<RneaBody>(m, U, 1, s, q, qd, qdd, tau);
 }
+// ---------------------------------------------------------------------------------------------
+// Frame kinematics of ONE serial chain of a static family, register resident (no per-link pose arrays, no run-time
+// indexing): the chain is walked link by link with the running world pose (R, o) and stops at the frame's joint fj
+// (uniform over the launch).  q points at the chain's planes; c0 / ntot place the chain inside a forest's outputs.
+// ---------------------------------------------------------------------------------------------
+template <class MP>
+MPCF_DI void chain_link_pose(const MP &m, int i, double c, double s, double *R, double *o)
+{
+    double Rl[9], Rn[9], on[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        Rl[3 * r + 0] = m.Rp(i, 3 * r) * c + m.Rp(i, 3 * r + 1) * s;
+        Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * c - m.Rp(i, 3 * r) * s;
+        Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
+    }
+    if (i == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rn[k] = Rl[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) on[k] = m.pp(i, k);
+    } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) Rn[3 * r + cc] = R[3 * r] * Rl[cc] + R[3 * r + 1] * Rl[3 + cc] + R[3 * r + 2] * Rl[6 + cc];
+            on[r] = o[r] + R[3 * r] * m.pp(i, 0) + R[3 * r + 1] * m.pp(i, 1) + R[3 * r + 2] * m.pp(i, 2);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = on[k];
+}
+
+// ee_pos, ee_rot of a frame carried by chain joint f.joint (bridge.hpp:106-111)
+template <int N>
+__global__ void __launch_bounds__(kThreads) fk_chain_kernel(const __grid_constant__ StaticParams<N> P, long U, FrameArg f, const double *q,
+                                                           double *pos, double *rot)
+{
+    const StaticModel<N, N> m{P};
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double R[9], o[3];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i > f.joint) break;
+        double s, c;
+        sincos(q[i * U + u], &s, &c);
+        chain_link_pose(m, i, c, s, R, o);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        pos[r * U + u] = o[r] + R[3 * r] * f.p[0] + R[3 * r + 1] * f.p[1] + R[3 * r + 2] * f.p[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rot[(3 * r + c) * U + u] = R[3 * r] * f.R[c] + R[3 * r + 1] * f.R[3 + c] + R[3 * r + 2] * f.R[6 + c];
+    }
+}
+
+// 6 x ntot LOCAL_WORLD_ALIGNED frame Jacobian (bridge.hpp:138-146): column c0 + i = [z_i x (p_f - o_i) ; z_i] for the chain
+// joints up to the frame's, zero elsewhere (other chains of a forest included)
+template <int N>
+__global__ void __launch_bounds__(kThreads) jac_chain_kernel(const __grid_constant__ StaticParams<N> P, long U, FrameArg f, const double *q,
+                                                            double *J, int ntot, int c0)
+{
+    const StaticModel<N, N> m{P};
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    double R[9], o[3], z[N][3], oj[N][3];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i > f.joint) break;
+        double s, c;
+        sincos(q[i * U + u], &s, &c);
+        chain_link_pose(m, i, c, s, R, o);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { z[i][r] = R[3 * r + 2]; oj[i][r] = o[r]; }
+    }
+    double pf[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) pf[r] = o[r] + R[3 * r] * f.p[0] + R[3 * r + 1] * f.p[1] + R[3 * r + 2] * f.p[2];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double col[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (i <= f.joint) {
+            const double d[3] = {pf[0] - oj[i][0], pf[1] - oj[i][1], pf[2] - oj[i][2]};
+            cross3(z[i], d, col);
+            col[3] = z[i][0]; col[4] = z[i][1]; col[5] = z[i][2];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) J[(long)(r * ntot + c0 + i) * U + u] = col[r];
+    }
+#pragma unroll 1
+    for (int i = 0; i < ntot; ++i)
+        if (i < c0 || i >= c0 + N)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) J[(long)(r * ntot + i) * U + u] = 0.0;
+}
+
+// out = J^T W without materialising J: the wrench, turned into the frame link's coordinates
+// ([R^T F ; R^T n + p x R^T F]: rotation chain only), is carried down the chain like a link force of the RNEA's inward
+// sweep and leaves its joint-axis component at every joint.  Rows of other chains are zero.
+template <int N>
+__global__ void __launch_bounds__(kThreads) jtw_chain_kernel(const __grid_constant__ StaticParams<N> P, long U, FrameArg f, const double *q,
+                                                            const double *W, double *out, int ntot, int c0)
+{
+    const StaticModel<N, N> m{P};
+    using D = Dyn<double, StaticModel<N, N>>;
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= U) return;
+    JointVar<double> jv[N];
+    double R[9], o[3];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i > f.joint) break;
+        sincos(q[i * U + u], &jv[i].s, &jv[i].c);
+        chain_link_pose(m, i, jv[i].c, jv[i].s, R, o);
+    }
+    double w[6], fl[6], t[3];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) w[r] = W[(long)r * U + u];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        fl[c] = R[c] * w[0] + R[3 + c] * w[1] + R[6 + c] * w[2];
+        fl[3 + c] = R[c] * w[3] + R[3 + c] * w[4] + R[6 + c] * w[5];
+    }
+    cross3(f.p, fl, t);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) fl[3 + c] += t[c];
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) {
+        if (i > f.joint) {
+            out[(long)(c0 + i) * U + u] = 0.0;
+            continue;
+        }
+        out[(long)(c0 + i) * U + u] = fl[5];
+        if (i > 0) {
+            double fp[6];
+            D::force_to_parent(m, i, jv[i], fl, fp);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) fl[r] = fp[r];
+        }
+    }
+#pragma unroll 1
+    for (int i = 0; i < ntot; ++i)
+        if (i < c0 || i >= c0 + N) out[(long)i * U + u] = 0.0;
+}
+
+// frame on a chain of a static family: which chain, its parameters, the frame with the joint index made chain-relative
+template <int L>
+static bool chain_frame(const LaunchModel &m, const FrameArg &f, const StaticParams<L> *&cp, FrameArg &fc, int &c0)
+{
+    if (f.joint < 0) return false;  // world-fixed frame: constant pose, the generic body handles it
+    const int c = f.joint / L;
+    c0 = c * L;
+    cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params) + c;
+    fc = f;
+    fc.joint = f.joint - c0;
+    return true;
+}
+
+template <int L>
+static cudaError_t frames_chain(int what, const LaunchModel &m, const FrameArg &f, long U, const double *q, const double *W, double *o0,
+                                double *o1, cudaStream_t s, bool &done)
+{
+    const StaticParams<L> *cp;
+    FrameArg fc;
+    int c0;
+    done = chain_frame<L>(m, f, cp, fc, c0);
+    if (!done) return cudaSuccess;
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    const double *qc = q + (size_t)c0 * U;
+    if (what == 0) fk_chain_kernel<L><<<gb, kThreads, 0, s>>>(*cp, U, fc, qc, o0, o1);
+    else if (what == 1) jac_chain_kernel<L><<<gb, kThreads, 0, s>>>(*cp, U, fc, qc, o0, m.n, c0);
+    else jtw_chain_kernel<L><<<gb, kThreads, 0, s>>>(*cp, U, fc, qc, W, o0, m.n, c0);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// what: 0 = pose, 1 = Jacobian, 2 = J^T W.  Returns true when a static-chain kernel took the call.
+static bool frames_static(int what, const LaunchModel &m, const FrameArg &f, long U, const double *q, const double *W, double *o0, double *o1,
+                          cudaStream_t s, cudaError_t &e)
+{
+    bool done = false;
+    switch (family_chain_len(m.fam)) {
+    case 3: e = frames_chain<3>(what, m, f, U, q, W, o0, o1, s, done); break;
+    case 6: e = frames_chain<6>(what, m, f, U, q, W, o0, o1, s, done); break;
+    case 7: e = frames_chain<7>(what, m, f, U, q, W, o0, o1, s, done); break;
+    default: break;
+    }
+    return done;
+}
+
 cudaError_t launch_fk(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *pos, double *rot, cudaStream_t s)
 {
+    if (U <= 0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (frames_static(0, m, f, U, q, nullptr, pos, rot, s, e)) return e;
     return dispatch<FkBody>(m, U, 1, s, f, q, pos, rot);
 }
 cudaError_t launch_jac(const LaunchModel &m, const FrameArg &f, long U, const double *q, double *J, cudaStream_t s)
 {
+    if (U <= 0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (frames_static(1, m, f, U, q, nullptr, J, nullptr, s, e)) return e;
     return dispatch<JacBody>(m, U, 1, s, f, q, J);
 }
 // Contact wrenches as external link forces of the RNEA (serial chain): W_e = [F ; n] is given in world axes at the frame
@@ -390,6 +588,10 @@ cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsig
                              double *qnext, double *Tnext, bool jtw_only, cudaStream_t s)
 {
     if (U <= 0) return cudaSuccess;
+    if (jtw_only && ee.nee == 1 && wsign == 1.0) {
+        cudaError_t e = cudaSuccess;
+        if (frames_static(2, m, ee.f[0], U, q, W, tau, nullptr, s, e)) return e;
+    }
     if (!jtw_only) {
         switch (family_chain_len(m.fam)) {
         case 3: return node_eval_chains<3>(m, ee, wsign, U, q, qd, qdd, W, T, h, zoh, tau, qnext, Tnext, s);

@@ -1,0 +1,28 @@
+import sys, os
+sys.path.insert(0, os.getcwd())
+import torch
+from mpc_fatigue_b200.evaluator import BatchEvaluator
+from mpc_fatigue_b200.model import Model, data_urdf
+from mpc_fatigue_b200.synth import synth_batch
+m = Model.from_urdf(data_urdf("pilz6"), armature=1e-2)
+ev = BatchEvaluator(m)
+lim = {k: m.export(k) for k in ("q_lo", "q_hi", "v_max", "tau_max")}
+B, N = 65536, 100
+q, qd, tau, f = synth_batch(lim, 0, B, N, device="cuda")
+U = B * N
+fr = m.frame_id("prbt_link_5")
+W = torch.randn((6, U), dtype=torch.float64, device="cuda")
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+pos = torch.empty((3, U), dtype=torch.float64, device="cuda"); rot = torch.empty((9, U), dtype=torch.float64, device="cuda")
+J = torch.empty((36, U), dtype=torch.float64, device="cuda")
+o = torch.empty((6, U), dtype=torch.float64, device="cuda")
+for name, fn, bytes_ in (("fk", lambda: ev.fk(fr, q, pos, rot), 18 * 8), ("jacobian", lambda: ev.jacobian(fr, q, J), 42 * 8),
+                         ("jac_t_wrench", lambda: ev.jac_t_wrench(fr, q, W, o), 18 * 8)):
+    ms = timed(fn)
+    print("%-14s %.3f ms  %.3e units/s  %.2f TB/s" % (name, ms, U / ms * 1e3, bytes_ * U / ms * 1e-9))
