@@ -125,6 +125,14 @@ struct CFromGlobal {
     MPCF_DI double operator()(int r, int c) const { return o[(2 * N * N + r * N + c) * 32]; }
 };
 
+// C held by the caller (a lambda over its register array)
+template <class F>
+struct CFromRegisters {
+    F f;
+    MPCF_DI void ready() const {}
+    MPCF_DI double operator()(int r, int c) const { return f(r, c); }
+};
+
 template <int N, int L, bool KSMEM>
 __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant__ StaticParams<N> P, long cnt, double *ws)
 {
@@ -163,26 +171,39 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
     }
 }
 
-// public fd-derivs entry for static families: thread = unit, qdd from ABA, then the analytic derivatives
-template <int N, int L>
+// public fd-derivs entry for static families, one serial chain per launch (joints [c0, c0 + N) of an ntot-joint forest; q, qd,
+// tau point at the chain's planes): forward dynamics through M = L D L^T, which also yields C = M^-1, then the
+// column-streamed derivative pass (run_cols) with C in registers.  Entries between different chains are written as 0.
+template <int N>
 __global__ void __launch_bounds__(kThreads) k_fd_derivs(const __grid_constant__ StaticParams<N> P, long U, const double *q, const double *qd,
-                                                       const double *tau, double *Ao, double *Bo, double *Co)
+                                                       const double *tau, double *Ao, double *Bo, double *Co, int ntot, int c0)
 {
-    const StaticModel<N, L> m{P};
+    const StaticModel<N, N> m{P};
     const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= U) return;
-    double a[N], b[N], c[N], qdd[N];
+    double a[N], b[N], c[N], qdd[N], Cv[N * (N + 1) / 2];
 #pragma unroll
     for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = tau[i * U + u]; }
-    Dyn<double, StaticModel<N, L>>::fd(m, a, b, c, qdd);
-    double A[N * N], B[N * N], C[N * N];
-    FdDerivs<StaticModel<N, L>, L>::run(m, a, b, qdd, A, B, C);
+    Dyn<double, StaticModel<N, N>>::template fd_crba<N, true>(m, a, b, c, qdd, Cv);
+    auto at = [&](int r, int cc) { return (size_t)((c0 + r) * ntot + c0 + cc) * U + u; };
 #pragma unroll
-    for (int k = 0; k < N * N; ++k) {
-        Ao[(size_t)k * U + u] = A[k];
-        Bo[(size_t)k * U + u] = B[k];
-        Co[(size_t)k * U + u] = C[k];
-    }
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int cc = 0; cc < N; ++cc) Co[at(r, cc)] = Cv[r >= cc ? r * (r + 1) / 2 + cc : cc * (cc + 1) / 2 + r];
+    auto cget = [&](int r, int cc) { return Cv[r * (r + 1) / 2 + cc]; };
+    CFromRegisters<decltype(cget)> Cs{cget};
+    auto emit = [&](int mat, int r, int cc, double v) { (mat == 0 ? Ao : Bo)[at(r, cc)] = v; };
+    extern __shared__ double link_slab[];
+    SharedLinkStore ks{link_slab + threadIdx.x, (int)blockDim.x};
+    FdDerivs<StaticModel<N, N>, N>::run_cols(m, a, b, qdd, Cs, emit, ks);
+#pragma unroll 1
+    for (int r = 0; r < N; ++r)
+#pragma unroll 1
+        for (int cc = 0; cc < ntot; ++cc)
+            if (cc < c0 || cc >= c0 + N) {
+                const size_t k = (size_t)((c0 + r) * ntot + cc) * U + u;
+                Ao[k] = 0.0; Bo[k] = 0.0; Co[k] = 0.0;
+            }
 }
 
 // inverse-dynamics derivatives for static families: dtau/dq, dtau/dqd, M at (q, qd, qdd); thread = unit
@@ -912,29 +933,32 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
     return cudaGetLastError();
 }
 
+template <int L>
+static cudaError_t fd_derivs_chains(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
+                                    double *C, cudaStream_t s)
+{
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params);
+    const cudaError_t e = cudaFuncSetAttribute(k_fd_derivs<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(L));
+    if (e != cudaSuccess) return e;
+    for (int c = 0; c < m.n / L; ++c) {
+        const size_t off = (size_t)c * L * U;
+        k_fd_derivs<L><<<gb, kThreads, link_slab_bytes(L), s>>>(cp[c], U, q + off, qd + off, tau + off, A, B, C, m.n, c * L);
+        g_launches.fetch_add(1);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
                              double *C, cudaStream_t s)
 {
     if (U <= 0) return cudaSuccess;
-    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
-    switch (m.fam) {
-    case FAM_CHAIN3:
-        k_fd_derivs<3, 3><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, tau, A, B, C);
-        break;
-    case FAM_CHAIN6:
-        k_fd_derivs<6, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, A, B, C);
-        break;
-    case FAM_FOREST12x6:
-        k_fd_derivs<12, 6><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<12> *>(m.static_params), U, q, qd, tau, A, B, C);
-        break;
-    case FAM_CHAIN7:
-        k_fd_derivs<7, 7><<<gb, kThreads, 0, s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, tau, A, B, C);
-        break;
-    default:
-        return dispatch<FdDerivsDualBody>(m, U, 3 * m.n, s, q, qd, tau, A, B, C);
+    switch (family_chain_len(m.fam)) {
+    case 3: return fd_derivs_chains<3>(m, U, q, qd, tau, A, B, C, s);
+    case 6: return fd_derivs_chains<6>(m, U, q, qd, tau, A, B, C, s);
+    case 7: return fd_derivs_chains<7>(m, U, q, qd, tau, A, B, C, s);
+    default: return dispatch<FdDerivsDualBody>(m, U, 3 * m.n, s, q, qd, tau, A, B, C);
     }
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
 }
 
 }  // namespace mpcf

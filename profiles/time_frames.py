@@ -26,3 +26,8 @@ for name, fn, bytes_ in (("fk", lambda: ev.fk(fr, q, pos, rot), 18 * 8), ("jacob
                          ("jac_t_wrench", lambda: ev.jac_t_wrench(fr, q, W, o), 18 * 8)):
     ms = timed(fn)
     print("%-14s %.3f ms  %.3e units/s  %.2f TB/s" % (name, ms, U / ms * 1e3, bytes_ * U / ms * 1e-9))
+
+Us = 1 << 20
+sl = [t[:, :Us].contiguous() for t in (q, qd, tau)]
+ms = timed(lambda: ev.fd_derivs(*sl))
+print("%-14s %.3f ms  %.3e units/s  (U = %d)" % ("fd_derivs", ms, Us / ms * 1e3, Us))
