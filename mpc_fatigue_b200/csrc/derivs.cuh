@@ -16,6 +16,11 @@
 //   dID_m/dqd_j =  S_m . (B_c,k S_j - 2 I_c,k xi_j),  k = max(m, j)
 //   M_mj        =  S_m . I_c,k S_j (+ armature on the diagonal)
 //
+// Two organisations of the same formulas, both for ONE serial chain (forests run chain by chain) and both streaming — the
+// forward pass computes kinematics only, the backward pass rebuilds each link from its child by undoing the joint, nothing
+// is accumulated per link or per matrix:  run_cols (forward-dynamics derivatives, C = M^-1 supplied by the caller) and
+// run_id_stream (inverse-dynamics derivatives and M, entry by entry).
+//
 // Derivation in DESIGN.md §4; checked against complex-step differentiation of the oracle's ABA
 // (tests/test_gpu_parity.py::test_fd_derivs).  There is no reference code for this (north-star addition).
 #pragma once
@@ -258,148 +263,6 @@ struct FdDerivs {
         }
     }
 
-    // A, B, C: row-major [N][N] (entries between different chains are written as 0)
-    // convenience wrapper writing row-major [N][N] arrays (entries between different chains are written as 0)
-    static MPCF_DI void run(const MP &m, const double *q, const double *qd, const double *qdd, double *A, double *B, double *C)
-    {
-#pragma unroll
-        for (int k = 0; k < N * N; ++k) { A[k] = 0.0; B[k] = 0.0; C[k] = 0.0; }
-        run_emit(m, q, qd, qdd, [&](int mat, int r, int c, double v) { (mat == 0 ? A : (mat == 1 ? B : C))[r * N + c] = v; });
-    }
-
-    // emit(mat, row, col, value) is called once for every same-chain entry of A (mat 0), B (1), C (2), column by column,
-    // as soon as the column is solved, so the caller can store it straight to memory instead of holding 3 n^2 values.
-    template <class Emit>
-    static MPCF_DI void run_emit(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit)
-    {
-        LocalLinkStore<N> ks;
-        run_emit_ks(m, q, qd, qdd, emit, ks);
-    }
-
-    // KS: where the per-link (S, xi, eta) live between the passes: thread-local arrays (LocalLinkStore) or a
-    // shared-memory slab with a conflict-free [slot][thread] layout (SharedLinkStore).
-    // SOLVE = true : emit A = dqdd/dq (mat 0), B = dqdd/dqd (1), C = M^-1 (2)              [forward-dynamics derivatives]
-    // SOLVE = false: emit dID/dq (mat 0), dID/dqd (1), M (2) at the given (q, qd, qdd)       [inverse-dynamics derivatives]
-    template <class Emit, class KS, bool SOLVE = true>
-    static MPCF_DI void run_emit_ks(const MP &m, const double *q, const double *qd, const double *qdd, Emit emit, KS &ks)
-    {
-        RigidInertiaW Iw[N];
-        double Hw[N][6], Fw[N][6], Bs[N][6];
-        double M[N][N], Dq[N][N], Dv[N][N];
-        double oR[9], o[3], v[6], a[6];
-        // ------------------------------------------------------------------ forward pass (world frame)
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (m.skip(i)) continue;  // never taken: one basic block per link (StaticModel::skip)
-            double s, c;
-            sincos(q[i], &s, &c);
-            LinkFwd Ki;
-            link_kin(m, i, c, s, qd[i], qdd[i], oR, o, v, a, Ki);
-            ks.put(i, Ki);
-            link_world(m, i, oR, o, v, a, Iw[i], Hw[i], Fw[i], Bs[i]);
-        }
-        // ------------------------------------------------------------------ composite + pairing pass
-#pragma unroll
-        for (int r = 0; r < N; ++r)
-#pragma unroll
-            for (int cI = 0; cI < N; ++cI) { M[r][cI] = 0.0; Dq[r][cI] = 0.0; Dv[r][cI] = 0.0; }
-        RigidInertiaW Ic;
-        double Hc[6], Fc[6], Bc[6];
-#pragma unroll
-        for (int k = N - 1; k >= 0; --k) {
-            if (m.skip(k)) continue;
-            const bool leaf = ((k + 1) % L) == 0;
-            const int c0 = (k / L) * L;  // first joint of this chain
-            if (leaf) {
-                Ic = Iw[k];
-#pragma unroll
-                for (int e = 0; e < 6; ++e) { Hc[e] = Hw[k][e]; Fc[e] = Fw[k][e]; Bc[e] = Bs[k][e]; }
-            } else {
-                Ic.m += Iw[k].m;
-#pragma unroll
-                for (int e = 0; e < 3; ++e) Ic.h[e] += Iw[k].h[e];
-#pragma unroll
-                for (int e = 0; e < 6; ++e) { Ic.Io[e] += Iw[k].Io[e]; Hc[e] += Hw[k][e]; Fc[e] += Fw[k][e]; Bc[e] += Bs[k][e]; }
-            }
-            LinkFwd Kk;
-            ks.get(k, Kk);
-            double rk[6], sk[3], gk[6], gvk[6];
-            pair_vectors(Ic, Hc, Fc, Bc, Kk, rk, sk, gk, gvk);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                if (j < c0 || j > k) continue;  // same chain, j <= k
-                LinkFwd Kj;
-                if (j == k) Kj = Kk; else ks.get(j, Kj);
-                const double mkj = dot6(rk, Kj.S);
-                M[k][j] = mkj;
-                M[j][k] = mkj;
-                Dq[k][j] = -(dot6(rk, Kj.eta) + dot3(sk, Kj.xi + 3));
-                Dv[k][j] = dot3(sk, Kj.S + 3) - 2.0 * dot6(rk, Kj.xi);
-                if (j < k) {
-                    Dq[j][k] = dot6(Kj.S, gk);
-                    Dv[j][k] = dot6(Kj.S, gvk);
-                }
-            }
-            M[k][k] += m.arm(k);
-        }
-        if (!SOLVE) {
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-#pragma unroll
-                for (int cI = 0; cI < N; ++cI) {
-                    if (r / L != cI / L) continue;
-                    emit(0, r, cI, Dq[r][cI]);
-                    emit(1, r, cI, Dv[r][cI]);
-                    emit(2, r, cI, M[r][cI]);
-                }
-            return;
-        }
-        // ------------------------------------------------------------------ per chain: LDL^T, C = M^-1, A = -C Dq, B = -C Dv
-#pragma unroll
-        for (int c0 = 0; c0 < N; c0 += L) {
-            double Lm[L][L], LD[L][L], Dinv[L];  // LD[i][k] = Lm[i][k] * D[k]
-            // M = Lm D Lm^T, unit lower-triangular Lm
-#pragma unroll
-            for (int j = 0; j < L; ++j) {
-                double d = M[c0 + j][c0 + j];
-#pragma unroll
-                for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
-                Dinv[j] = 1.0 / d;
-#pragma unroll
-                for (int i = j + 1; i < L; ++i) {
-                    double e = M[c0 + i][c0 + j];
-#pragma unroll
-                    for (int k = 0; k < j; ++k) e -= Lm[i][k] * LD[j][k];
-                    LD[i][j] = e;
-                    Lm[i][j] = e * Dinv[j];
-                }
-            }
-            // solve M x = b for 3 families of right-hand sides
-#pragma unroll
-            for (int col = 0; col < 3 * L; ++col) {
-                double x[L];
-#pragma unroll
-                for (int i = 0; i < L; ++i) {
-                    if (col < L) x[i] = -Dq[c0 + i][c0 + col];
-                    else if (col < 2 * L) x[i] = -Dv[c0 + i][c0 + col - L];
-                    else x[i] = (i == col - 2 * L) ? 1.0 : 0.0;
-                }
-#pragma unroll
-                for (int i = 0; i < L; ++i)
-#pragma unroll
-                    for (int k = 0; k < i; ++k) x[i] -= Lm[i][k] * x[k];
-#pragma unroll
-                for (int i = 0; i < L; ++i) x[i] *= Dinv[i];
-#pragma unroll
-                for (int i = L - 1; i >= 0; --i)
-#pragma unroll
-                    for (int k = i + 1; k < L; ++k) x[i] -= Lm[k][i] * x[k];
-                const int cj = c0 + col % L;
-#pragma unroll
-                for (int i = 0; i < L; ++i) emit(col / L, c0 + i, cj, x[i]);
-            }
-        }
-    }
     // adds link k (the last link of the chain starts the sums) to the composites of the sub-chain rooted at k
     static MPCF_DI void accumulate_link(const MP &m, int k, const double *R, const double *o, const double *v, const double *a,
                                         RigidInertiaW &Ic, double *Hc, double *Fc, double *Bc)

@@ -206,48 +206,47 @@ __global__ void __launch_bounds__(kThreads) k_fd_derivs(const __grid_constant__ 
             }
 }
 
-// inverse-dynamics derivatives for static families: dtau/dq, dtau/dqd, M at (q, qd, qdd); thread = unit
-template <int N, int L>
+// inverse-dynamics derivatives for static families, one serial chain per launch (joints [c0, c0 + N) of an ntot-joint
+// forest): dtau/dq, dtau/dqd, M at (q, qd, qdd), streamed entry by entry (run_id_stream); thread = unit
+template <int N>
 __global__ void __launch_bounds__(kThreads) k_rnea_derivs(const __grid_constant__ StaticParams<N> P, long U, const double *q, const double *qd,
-                                                         const double *qdd, double *Dq, double *Dv, double *Mo)
+                                                         const double *qdd, double *Dq, double *Dv, double *Mo, int ntot, int c0)
 {
-    const StaticModel<N, L> m{P};
+    const StaticModel<N, N> m{P};
     const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= U) return;
     double a[N], b[N], c[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { a[i] = q[i * U + u]; b[i] = qd[i * U + u]; c[i] = qdd ? qdd[i * U + u] : 0.0; }
-    // cross-chain entries are structurally zero
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-        for (int cc = 0; cc < N; ++cc)
-            if (r / L != cc / L) { Dq[(size_t)(r * N + cc) * U + u] = 0.0; Dv[(size_t)(r * N + cc) * U + u] = 0.0; Mo[(size_t)(r * N + cc) * U + u] = 0.0; }
-    if constexpr (N == L) {
-        extern __shared__ double link_slab[];
-        SharedLinkStore ks{link_slab + threadIdx.x, (int)blockDim.x};
-        struct Hooks {
-            double *Dq, *Dv, *Mo;
-            long U, u;
-            MPCF_DI void link(int, const double *, const double *) const {}
-            MPCF_DI void pair(int k, int j, const LinkFwd &, const LinkFwd &, double dqkj, double dqjk, double dvkj, double dvjk, double mkj) const
-            {
-                Dq[(size_t)(k * N + j) * U + u] = dqkj;
-                Dv[(size_t)(k * N + j) * U + u] = dvkj;
-                Mo[(size_t)(k * N + j) * U + u] = mkj;
-                if (j < k) {
-                    Dq[(size_t)(j * N + k) * U + u] = dqjk;
-                    Dv[(size_t)(j * N + k) * U + u] = dvjk;
-                    Mo[(size_t)(j * N + k) * U + u] = mkj;
-                }
+    extern __shared__ double link_slab[];
+    SharedLinkStore ks{link_slab + threadIdx.x, (int)blockDim.x};
+    struct Hooks {
+        double *Dq, *Dv, *Mo;
+        long U, u;
+        int ntot, c0;
+        MPCF_DI size_t at(int r, int cc) const { return (size_t)((c0 + r) * ntot + c0 + cc) * U + u; }
+        MPCF_DI void link(int, const double *, const double *) const {}
+        MPCF_DI void pair(int k, int j, const LinkFwd &, const LinkFwd &, double dqkj, double dqjk, double dvkj, double dvjk, double mkj) const
+        {
+            Dq[at(k, j)] = dqkj;
+            Dv[at(k, j)] = dvkj;
+            Mo[at(k, j)] = mkj;
+            if (j < k) {
+                Dq[at(j, k)] = dqjk;
+                Dv[at(j, k)] = dvjk;
+                Mo[at(j, k)] = mkj;
             }
-        } hooks{Dq, Dv, Mo, U, u};
-        FdDerivs<StaticModel<N, L>, L>::run_id_stream(m, a, b, c, hooks, ks);
-    } else {
-        LocalLinkStore<N> ks;
-        auto emit = [&](int mat, int r, int cc, double v) { (mat == 0 ? Dq : (mat == 1 ? Dv : Mo))[(size_t)(r * N + cc) * U + u] = v; };
-        FdDerivs<StaticModel<N, L>, L>::template run_emit_ks<decltype(emit), LocalLinkStore<N>, false>(m, a, b, c, emit, ks);
-    }
+        }
+    } hooks{Dq, Dv, Mo, U, u, ntot, c0};
+    FdDerivs<StaticModel<N, N>, N>::run_id_stream(m, a, b, c, hooks, ks);
+#pragma unroll 1
+    for (int r = 0; r < N; ++r)
+#pragma unroll 1
+        for (int cc = 0; cc < ntot; ++cc)  // entries between different chains are structurally zero
+            if (cc < c0 || cc >= c0 + N) {
+                const size_t k = (size_t)((c0 + r) * ntot + cc) * U + u;
+                Dq[k] = 0.0; Dv[k] = 0.0; Mo[k] = 0.0;
+            }
 }
 
 // Reference-mode torque rows tau = ID(q, qd, qdd) + wsign * sum_e J_e^T W_e (force_optimization_pilz_6DOF.py:134,
@@ -904,33 +903,32 @@ cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double 
     }
 }
 
+template <int L>
+static cudaError_t rnea_derivs_chains(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
+                                      double *M, cudaStream_t s)
+{
+    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
+    const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.n == L ? m.static_params : m.chain_params);
+    const cudaError_t e = cudaFuncSetAttribute(k_rnea_derivs<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(L));
+    if (e != cudaSuccess) return e;
+    for (int c = 0; c < m.n / L; ++c) {
+        const size_t off = (size_t)c * L * U;
+        k_rnea_derivs<L><<<gb, kThreads, link_slab_bytes(L), s>>>(cp[c], U, q + off, qd + off, qdd ? qdd + off : nullptr, Dq, Dv, M, m.n, c * L);
+        g_launches.fetch_add(1);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
                                double *M, cudaStream_t s)
 {
     if (U <= 0) return cudaSuccess;
-    const unsigned gb = (unsigned)((U + kThreads - 1) / kThreads);
-    cudaError_t e;
-    switch (m.fam) {
-    case FAM_CHAIN3:
-        e = cudaFuncSetAttribute(k_rnea_derivs<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(3));
-        if (e != cudaSuccess) return e;
-        k_rnea_derivs<3, 3><<<gb, kThreads, link_slab_bytes(3), s>>>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
-        break;
-    case FAM_CHAIN6:
-        e = cudaFuncSetAttribute(k_rnea_derivs<6, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(6));
-        if (e != cudaSuccess) return e;
-        k_rnea_derivs<6, 6><<<gb, kThreads, link_slab_bytes(6), s>>>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
-        break;
-    case FAM_CHAIN7:
-        e = cudaFuncSetAttribute(k_rnea_derivs<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, link_slab_bytes(7));
-        if (e != cudaSuccess) return e;
-        k_rnea_derivs<7, 7><<<gb, kThreads, link_slab_bytes(7), s>>>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, qdd, Dq, Dv, M);
-        break;
-    default:
-        return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
+    switch (family_chain_len(m.fam)) {
+    case 3: return rnea_derivs_chains<3>(m, U, q, qd, qdd, Dq, Dv, M, s);
+    case 6: return rnea_derivs_chains<6>(m, U, q, qd, qdd, Dq, Dv, M, s);
+    case 7: return rnea_derivs_chains<7>(m, U, q, qd, qdd, Dq, Dv, M, s);
+    default: return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
     }
-    g_launches.fetch_add(1);
-    return cudaGetLastError();
 }
 
 template <int L>
