@@ -481,37 +481,38 @@ struct WrenchExt {
     double wsign;
     MPCF_DI void link(const StaticModel<N, N> &m, int i, const JointVar<double> &jv, double *f)
     {
-        if (NEE == 0) return;
-        double Rl[9], Rn[9];
+        if constexpr (NEE > 0) {
+            double Rl[9], Rn[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            Rl[3 * r + 0] = m.Rp(i, 3 * r) * jv.c + m.Rp(i, 3 * r + 1) * jv.s;
-            Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * jv.c - m.Rp(i, 3 * r) * jv.s;
-            Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                Rn[3 * r + c] = (i == 0) ? Rl[3 * r + c] : R[3 * r] * Rl[c] + R[3 * r + 1] * Rl[3 + c] + R[3 * r + 2] * Rl[6 + c];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-#pragma unroll
-        for (int e = 0; e < NEE; ++e)
-            if (je[e] == i) {
-                double Fl[3], nl[3], t[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    Fl[c] = R[c] * Wl[e][0] + R[3 + c] * Wl[e][1] + R[6 + c] * Wl[e][2];
-                    nl[c] = R[c] * Wl[e][3] + R[3 + c] * Wl[e][4] + R[6 + c] * Wl[e][5];
-                }
-                cross3(pl[e], Fl, t);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    f[c] += wsign * Fl[c];
-                    f[3 + c] += wsign * (nl[c] + t[c]);
-                }
+            for (int r = 0; r < 3; ++r) {
+                Rl[3 * r + 0] = m.Rp(i, 3 * r) * jv.c + m.Rp(i, 3 * r + 1) * jv.s;
+                Rl[3 * r + 1] = m.Rp(i, 3 * r + 1) * jv.c - m.Rp(i, 3 * r) * jv.s;
+                Rl[3 * r + 2] = m.Rp(i, 3 * r + 2);
             }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    Rn[3 * r + c] = (i == 0) ? Rl[3 * r + c] : R[3 * r] * Rl[c] + R[3 * r + 1] * Rl[3 + c] + R[3 * r + 2] * Rl[6 + c];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+#pragma unroll
+            for (int e = 0; e < NEE; ++e)
+                if (je[e] == i) {
+                    double Fl[3], nl[3], t[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        Fl[c] = R[c] * Wl[e][0] + R[3 + c] * Wl[e][1] + R[6 + c] * Wl[e][2];
+                        nl[c] = R[c] * Wl[e][3] + R[3 + c] * Wl[e][4] + R[6 + c] * Wl[e][5];
+                    }
+                    cross3(pl[e], Fl, t);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        f[c] += wsign * Fl[c];
+                        f[3 + c] += wsign * (nl[c] + t[c]);
+                    }
+                }
+        }
     }
 };
 
@@ -605,7 +606,7 @@ cudaError_t launch_node_eval(const LaunchModel &m, const EeArgs &ee, double wsig
 cudaError_t launch_node_eval_jvp_dual(const LaunchModel &m, const EeArgs &ee, double wsign, long U, const double *q, const double *qd,
                                  const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s)
 {
-    return dispatch<NodeEvalJvpBody>(m, U, 2 * m.n, s, ee, wsign, q, qd, qdd, W, dtau_dq, dtau_dqd);
+    return dispatch_generic<NodeEvalJvpBody>(m, U, 2 * m.n, s, ee, wsign, q, qd, qdd, W, dtau_dq, dtau_dqd);
 }
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
                                  const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,

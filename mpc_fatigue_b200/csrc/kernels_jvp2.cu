@@ -927,7 +927,7 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
     case 3: return rnea_derivs_chains<3>(m, U, q, qd, qdd, Dq, Dv, M, s);
     case 6: return rnea_derivs_chains<6>(m, U, q, qd, qdd, Dq, Dv, M, s);
     case 7: return rnea_derivs_chains<7>(m, U, q, qd, qdd, Dq, Dv, M, s);
-    default: return dispatch<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
+    default: return dispatch_generic<RneaDerivsDualBody>(m, U, 3 * m.n, s, q, qd, qdd, Dq, Dv, M);
     }
 }
 
@@ -955,7 +955,7 @@ cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, cons
     case 3: return fd_derivs_chains<3>(m, U, q, qd, tau, A, B, C, s);
     case 6: return fd_derivs_chains<6>(m, U, q, qd, tau, A, B, C, s);
     case 7: return fd_derivs_chains<7>(m, U, q, qd, tau, A, B, C, s);
-    default: return dispatch<FdDerivsDualBody>(m, U, 3 * m.n, s, q, qd, tau, A, B, C);
+    default: return dispatch_generic<FdDerivsDualBody>(m, U, 3 * m.n, s, q, qd, tau, A, B, C);
     }
 }
 

@@ -107,6 +107,20 @@ __global__ void __launch_bounds__(kThreads, GenericMinBlocks<Body>::value) gener
     if (u < U) Body::run(m, u, U, args...);
 }
 
+// Bodies that only the run-time-topology families use (the static families have dedicated kernels for the same entry):
+// no static_kernel instantiations, so they cost neither compile time nor binary size.
+template <class Body, class... Args>
+static cudaError_t dispatch_generic(const LaunchModel &m, long U, int grid_y, cudaStream_t s, Args... args)
+{
+    if (U <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((U + kThreads - 1) / kThreads), (unsigned)grid_y), block(kThreads);
+    if (m.fam == FAM_GENERIC16) generic_kernel<16, Body, Args...><<<grid, block, blob_smem_bytes(m.n), s>>>(m.blob, U, args...);
+    else if (m.fam == FAM_GENERIC64) generic_kernel<MPCF_MAX_DOF, Body, Args...><<<grid, block, blob_smem_bytes(m.n), s>>>(m.blob, U, args...);
+    else return cudaErrorInvalidValue;
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 template <class Body, class... Args>
 static cudaError_t dispatch(const LaunchModel &m, long U, int grid_y, cudaStream_t s, Args... args)
 {
