@@ -29,9 +29,14 @@ template <int N>
 struct WsLayout {
     static constexpr int kTile = 32;
     static constexpr int kPlanes2 = 3 * N * N;                       // A, B, C
-    static constexpr int kPlanes1 = 4 * N;                           // q_s, qd_s, qdd_s, fdot_s
+    static constexpr int kPlanes1 = 4 * N;                           // qd_s, qdd_s, fdot_s, q_s
+    // plane offsets inside the stage-state block; q_s comes last: the chain-rule kernel does not use it and leaves it out
+    // of its bulk copies
+    static constexpr int kQd = 0, kQdd = N, kFd = 2 * N, kQ = 3 * N;
     static constexpr int kStageDoubles = (kPlanes2 + kPlanes1) * kTile;
     static constexpr unsigned kStageBytes = kStageDoubles * sizeof(double);
+    static constexpr int kRingDoubles = (kPlanes2 + 3 * N) * kTile;  // what one ring slot of the chain-rule kernel holds
+    static constexpr unsigned kRingBytes = kRingDoubles * sizeof(double);
     static constexpr int kUnitDoubles = 4 * (kPlanes2 + kPlanes1);
     // chunk of (tile, stage)
     static MPCF_DI size_t chunk(long tile, int s) { return ((size_t)tile * 4 + s) * kStageDoubles; }
@@ -84,10 +89,10 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            __stcs(w + i * 32, xs[i]);
-            __stcs(w + (N + i) * 32, xs[N + i]);
-            __stcs(w + (2 * N + i) * 32, k[N + i]);
-            __stcs(w + (3 * N + i) * 32, k[2 * N + i]);
+            __stcs(w + (W::kQ + i) * 32, xs[i]);
+            __stcs(w + (W::kQd + i) * 32, xs[N + i]);
+            __stcs(w + (W::kQdd + i) * 32, k[N + i]);
+            __stcs(w + (W::kFd + i) * 32, k[2 * N + i]);
         }
         const double a = h * wt, c = h * cs;
 #pragma unroll
@@ -146,9 +151,9 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
     double q[N], qd[N], qdd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        q[i] = __ldcs(w + i * 32);
-        qd[i] = __ldcs(w + (N + i) * 32);
-        qdd[i] = __ldcs(w + (2 * N + i) * 32);
+        q[i] = __ldcs(w + (W::kQ + i) * 32);
+        qd[i] = __ldcs(w + (W::kQd + i) * 32);
+        qdd[i] = __ldcs(w + (W::kQdd + i) * 32);
     }
     // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
     auto emit = [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); };
@@ -435,14 +440,14 @@ struct ColumnState {
         const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double qds = w1[(N + i) * 32];
+            const double qds = w1[(WsLayout<N>::kQd + i) * 32];
             double kf = 2.0 * P.fat[i][1] * P.fat[i][3] * qds * Xv[i] - P.fat[i][0] * Xf[i];
             if (i == jt) kf += ktau;
             double yq = h * Xv[i], yf = h * kf, yv = h * nv[i];
             if (isdt) {
                 yq += qds;
-                yv += w1[(2 * N + i) * 32];
-                yf += w1[(3 * N + i) * 32];
+                yv += w1[(WsLayout<N>::kQdd + i) * 32];
+                yf += w1[(WsLayout<N>::kFd + i) * 32];
             }
             aq[i] = fma(wt, yq, aq[i]);
             av[i] = fma(wt, yv, av[i]);
@@ -603,8 +608,8 @@ MPCF_DI void tma_issue(unsigned item, double *buf, unsigned long long *full, uns
     const unsigned slot = item % NBUF, round = item / NBUF;
     const long t = bid + (long)(item / 4) * nblk;
     mbar_wait(&empty[slot], (round & 1) ^ 1);
-    mbar_arrive_expect_tx(&full[slot], W::kStageBytes);
-    bulk_g2s(buf + (size_t)slot * W::kStageDoubles, ws + W::chunk(t, item & 3), W::kStageBytes, &full[slot]);
+    mbar_arrive_expect_tx(&full[slot], W::kRingBytes);
+    bulk_g2s(buf + (size_t)slot * W::kRingDoubles, ws + W::chunk(t, item & 3), W::kRingBytes, &full[slot]);
 }
 
 // Persistent chain-rule kernel for N <= 6.  CPW = Jacobian columns per consumer thread (1 or 2); NW consumer warps.
@@ -620,7 +625,7 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
     constexpr int NW = (NC + CPW - 1) / CPW;  // consumer warps
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *buf = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NBUF * W::kStageBytes);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NBUF * W::kRingBytes);
     unsigned long long *empty = full + NBUF;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long ntiles = (cnt + 31) / 32;
@@ -654,7 +659,7 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
             if (producer && it + NBUF - 1 < nitems) tma_issue<W, NBUF>(it + NBUF - 1, buf, full, empty, ws, blockIdx.x, gridDim.x);
             const unsigned slot = it % NBUF, round = it / NBUF;
             mbar_wait(&full[slot], round & 1);
-            const double *w = buf + (size_t)slot * W::kStageDoubles + lane;
+            const double *w = buf + (size_t)slot * W::kRingDoubles + lane;
             if (CPW == 2) ColumnState<N, L>::stage2(a, b, P, s, w, h);
             else a.stage(P, s, w, h);
             __syncwarp();
@@ -750,13 +755,14 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
                             cudaStream_t s, int ntot = N, int c0 = 0)
 {
     using W = WsLayout<N>;
-    // chain-rule kernel: bulk-copy ring as deep as 227 KB of shared memory allows; 3 N + 1 column warps of 96 registers fit
-    // the register file up to N = 6, longer chains run two columns per thread
+    // chain-rule kernel: bulk-copy ring of up to 5 slots (a deeper ring takes the shared-memory carve-out from L1, which the
+    // streaming Jacobian stores want); 3 N + 1 column warps of 96 registers fit the register file up to N = 6, longer chains
+    // run two columns per thread
     constexpr bool kTma = N <= 7;
-    constexpr int kRingMax = (227 * 1024 - 256) / (int)W::kStageBytes;
-    constexpr int NBUF = kTma ? (kRingMax > 6 ? 6 : kRingMax) : 0;
+    constexpr int kRingMax = (227 * 1024 - 256) / (int)W::kRingBytes;
+    constexpr int NBUF = kTma ? (kRingMax > 5 ? 5 : kRingMax) : 0;  // measured on chain6: 5 slots 11.74 ms, 4: 11.89, 6: 12.08, 7: 12.93 (L1 gets what the ring leaves)
     constexpr int kCpwDefault = (3 * N + 1 <= 19) ? 1 : 2;
-    constexpr size_t smem = (size_t)NBUF * W::kStageBytes + 2 * NBUF * sizeof(unsigned long long);
+    constexpr size_t smem = (size_t)NBUF * W::kRingBytes + 2 * NBUF * sizeof(unsigned long long);
     // derivative kernel: 2 blocks per SM with the link slab in shared memory
     constexpr int kK2Threads = (2 * (18 * (N - 1) + N * (N + 1) / 2) * kThreads * (int)sizeof(double) <= 227 * 1024) ? kThreads : 96;
     constexpr int kK2Slab = (18 * (N - 1) + N * (N + 1) / 2) * kK2Threads * (int)sizeof(double);
