@@ -31,3 +31,10 @@ Us = 1 << 20
 sl = [t[:, :Us].contiguous() for t in (q, qd, tau)]
 ms = timed(lambda: ev.fd_derivs(*sl))
 print("%-14s %.3f ms  %.3e units/s  (U = %d)" % ("fd_derivs", ms, Us / ms * 1e3, Us))
+q0, qd0, f0 = (t[:, :B].contiguous() for t in (q, 0.2 * qd, f))
+ms = timed(lambda: ev.rollout_rk4(q0, qd0, f0, 0.3 * tau, N, 0.02), reps=3)
+print("%-14s %.3f ms  %.3e rollout-steps/s  (B = %d scenarios x N = %d steps, one thread per scenario)" % ("rollout", ms, U / ms * 1e3, B, N))
+ms = timed(lambda: ev.aba(q, qd, tau))
+print("%-14s %.3f ms  %.3e units/s" % ("fwd dynamics", ms, U / ms * 1e3))
+ms = timed(lambda: ev.step_rk4(q, qd, tau, f, 0.02))
+print("%-14s %.3f ms  %.3e units/s" % ("step_rk4", ms, U / ms * 1e3))
