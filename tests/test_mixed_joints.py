@@ -1,0 +1,82 @@
+"""A hand-written URDF (tests/golden/mixed_joints.urdf — not from the reference) with what the Pilz models do not have:
+prismatic and continuous joints, joint axes off the local z, a fixed joint whose child carries inertia, a branch.
+
+CPU: the C++ and the Python loader agree, and the oracle's gravity torques equal the gradient of the potential energy
+computed independently from frame kinematics and the URDF's own inertial origins (this pins axis normalisation, the
+fixed-joint merge and the sign conventions without using the dynamics code).  GPU: parity on the same model."""
+import os
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, oracle_model_from_export, random_inputs, rel_err_rows
+from mpc_fatigue_b200.model import Model
+from oracle.pyoracle import Oracle
+from oracle.urdf_model import load_urdf
+
+XML = open(os.path.join(ROOT, "tests", "golden", "mixed_joints.urdf")).read()
+
+
+def test_loaders_agree_on_mixed_joint_types():
+    m, o = Model.from_urdf(XML, armature=1e-3), load_urdf(XML, armature=1e-3)
+    a = o.arrays()
+    assert m.n == 3 and m.joint_names == ["slide", "swing", "spin"] and m.kernel_family == "generic16"
+    assert m.export("jtype").tolist() == [1, 0, 0] and m.export("parent").tolist() == [-1, 0, 0]
+    for k in ("parent", "jtype", "fparent", "Rp", "pp", "mass", "mc", "Io", "fR", "fp", "q_lo", "q_hi", "v_max", "tau_max"):
+        assert np.abs(m.export(k).reshape(-1).astype(float) - a[k].reshape(-1).astype(float)).max() < 1e-15, k
+    assert abs(m.export("mass")[1] - 1.9) < 1e-15  # arm + the tool behind the fixed joint
+
+
+def _potential_energy(orc, om, q):
+    """U(q) = -sum_i m_i g . c_i(q) with c_i the world COM of every URDF link that has mass, from frame FK only."""
+    g = np.array([0.0, 0.0, -9.81])
+    U = np.zeros(q.shape[1])
+    for link in ET.fromstring(XML).findall("link"):
+        ine = link.find("inertial")
+        if ine is None:
+            continue
+        mass = float(ine.find("mass").get("value"))
+        org = ine.find("origin")
+        com = np.array([float(v) for v in (org.get("xyz") if org is not None and org.get("xyz") else "0 0 0").split()])
+        pos, rot = orc.fk(om.frame_names.index(link.get("name")), q)
+        c = pos + np.einsum("iju,j->iu", rot.reshape(3, 3, -1), com)
+        U -= mass * (g @ c)
+    return U
+
+
+def test_gravity_torque_is_the_potential_gradient():
+    om = load_urdf(XML, armature=0.0)
+    orc = Oracle(om)
+    rng = np.random.default_rng(2)
+    q = np.ascontiguousarray(rng.uniform(-1.0, 1.0, (3, 40)))
+    tau_g = orc.rnea(q, np.zeros_like(q), None)
+    h = 1e-6
+    for j in range(3):
+        dq = np.zeros_like(q)
+        dq[j] = h
+        dU = (_potential_energy(orc, om, q + dq) - _potential_energy(orc, om, q - dq)) / (2 * h)
+        assert np.abs(tau_g[j] - dU).max() < 1e-7 * max(1.0, np.abs(dU).max()), j
+
+
+@pytest.mark.gpu
+def test_gpu_parity_on_mixed_joint_model():
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    m = Model.from_urdf(XML, armature=1e-3)
+    om = oracle_model_from_export(m)
+    orc, ev = Oracle(om), BatchEvaluator(m)
+    U = 97
+    q, qd, tau, f, qdd = random_inputs(om, U, seed=5)
+    d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f, qdd)]
+    assert rel_err_rows(ev.rnea(d[0], d[1], d[4]).cpu().numpy(), orc.rnea(q, qd, qdd)) < 1e-9
+    assert rel_err_rows(ev.aba(d[0], d[1], d[2]).cpu().numpy(), orc.aba(q, qd, tau)) < 1e-9
+    for fr in range(m.nframes):
+        pos, rot = orc.fk(fr, q)
+        gp, gr = ev.fk(fr, d[0])
+        assert np.abs(gp.cpu().numpy() - pos).max() < 1e-12 and np.abs(gr.cpu().numpy() - rot).max() < 1e-12
+        assert np.abs(ev.jacobian(fr, d[0]).cpu().numpy() - orc.jacobian(fr, q)).max() < 1e-12
+    ref = orc.step_rk4_jvp(q, qd, tau, f, 0.01)
+    got = ev.step_rk4_jvp(d[0], d[1], d[2], d[3], 0.01)
+    for g_, r_ in zip(got, ref):
+        assert np.abs(g_.cpu().numpy() - r_).max() < 1e-9 * max(1.0, np.abs(r_).max())
