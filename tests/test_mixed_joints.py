@@ -80,3 +80,72 @@ def test_gpu_parity_on_mixed_joint_model():
     got = ev.step_rk4_jvp(d[0], d[1], d[2], d[3], 0.01)
     for g_, r_ in zip(got, ref):
         assert np.abs(g_.cpu().numpy() - r_).max() < 1e-9 * max(1.0, np.abs(r_).max())
+
+
+def _rpy(r, p, y):
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                     [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]])
+
+
+def _energies(orc, om, xml, q, qd):
+    """(2 x kinetic energy, potential energy) of every unit from the URDF text and frame kinematics only."""
+    n, U = q.shape
+    g = np.array([0.0, 0.0, -9.81])
+    ke2, pe = np.zeros(U), np.zeros(U)
+    for link in ET.fromstring(xml).findall("link"):
+        ine = link.find("inertial")
+        if ine is None or link.get("name") not in om.frame_names:
+            continue
+        mass = float(ine.find("mass").get("value"))
+        org = ine.find("origin")
+        xyz = np.array([float(v) for v in ((org.get("xyz") if org is not None else None) or "0 0 0").split()])
+        rpy = [float(v) for v in ((org.get("rpy") if org is not None else None) or "0 0 0").split()]
+        I = ine.find("inertia")
+        Ic = np.array([[float(I.get("ixx")), float(I.get("ixy")), float(I.get("ixz"))],
+                       [float(I.get("ixy")), float(I.get("iyy")), float(I.get("iyz"))],
+                       [float(I.get("ixz")), float(I.get("iyz")), float(I.get("izz"))]])
+        Ic = _rpy(*rpy) @ Ic @ _rpy(*rpy).T  # inertia in link axes
+        fr = om.frame_names.index(link.get("name"))
+        pos, rot = orc.fk(fr, q)
+        J = orc.jacobian(fr, q).reshape(6, n, U)  # LOCAL_WORLD_ALIGNED at the link origin
+        tw = np.einsum("rju,ju->ru", J, qd)
+        R = rot.reshape(3, 3, U)
+        w = tw[3:]
+        r_c = np.einsum("iju,j->ui", R, xyz)
+        vc = tw[:3] + np.cross(w.T, r_c).T
+        wl = np.einsum("jiu,ju->iu", R, w)  # angular velocity in link axes
+        ke2 += mass * (vc * vc).sum(0) + np.einsum("iu,ij,ju->u", wl, Ic, wl)
+        pe -= mass * (g @ (pos + r_c.T))
+    return ke2, pe
+
+
+@pytest.mark.parametrize("which", ["mixed", "pilz6"])
+def test_mass_matrix_and_power_balance_from_frame_kinematics(which):
+    """Two checks of the oracle's inverse dynamics against quantities built from the URDF text and frame kinematics only:
+    q̇ᵀ M(q) q̇ = sum over links of m |v_c|² + ωᵀ I_c ω (pins the inertial terms), and along any motion
+    q̇ᵀ ID(q, q̇, q̈) = d/dt (kinetic + potential energy) (pins the Coriolis / centrifugal and gravity terms)."""
+    from mpc_fatigue_b200.model import data_urdf
+    xml = XML if which == "mixed" else data_urdf("pilz6")
+    om = load_urdf(xml, armature=0.0)
+    orc = Oracle(om)
+    n, U = om.n, 12
+    rng = np.random.default_rng(9)
+    q = np.ascontiguousarray(rng.uniform(-1.0, 1.0, (n, U)))
+    qd = np.ascontiguousarray(rng.uniform(-1.0, 1.0, (n, U)))
+    qdd = np.ascontiguousarray(rng.uniform(-2.0, 2.0, (n, U)))
+    z = np.zeros_like(q)
+    bias = orc.rnea(q, z, None)
+    M = np.stack([orc.rnea(q, z, np.ascontiguousarray(np.eye(n)[:, [j]].repeat(U, 1))) - bias for j in range(n)], axis=1)  # [n, n, U]
+    ke2, _ = _energies(orc, om, xml, q, qd)
+    assert np.abs(np.einsum("iu,iju,ju->u", qd, M, qd) - ke2).max() < 1e-10 * np.abs(ke2).max()
+    h = 1e-5
+    E = []
+    for sgn in (+1.0, -1.0):
+        qs = np.ascontiguousarray(q + sgn * h * qd + 0.5 * h * h * qdd)
+        k2, pe = _energies(orc, om, xml, qs, np.ascontiguousarray(qd + sgn * h * qdd))
+        E.append(0.5 * k2 + pe)
+    power = (qd * orc.rnea(q, qd, qdd)).sum(0)
+    dE = (E[0] - E[1]) / (2 * h)
+    assert np.abs(power - dE).max() < 1e-6 * max(1.0, np.abs(dE).max())
