@@ -149,3 +149,52 @@ def test_mass_matrix_and_power_balance_from_frame_kinematics(which):
     power = (qd * orc.rnea(q, qd, qdd)).sum(0)
     dE = (E[0] - E[1]) / (2 * h)
     assert np.abs(power - dE).max() < 1e-6 * max(1.0, np.abs(dE).max())
+
+
+@pytest.mark.gpu
+def test_gpu_power_balance_at_scale():
+    """The same power balance with every term from the CUDA path (RNEA, frame poses and Jacobians through the C-ABI) on 2^20
+    units of the Pilz 6-DOF model: a size-independent property that involves neither the oracle nor any CPU arithmetic."""
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import data_urdf
+    xml = data_urdf("pilz6")
+    m = Model.from_urdf(xml, armature=0.0)
+    ev = BatchEvaluator(m)
+    n, U = m.n, 1 << 20
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    rnd = lambda s: (torch.rand((n, U), dtype=torch.float64, device="cuda", generator=gen) * 2.0 - 1.0) * s
+    q, qd, qdd = rnd(1.5), rnd(1.0), rnd(2.0)
+    links = []
+    for link in ET.fromstring(xml).findall("link"):
+        ine = link.find("inertial")
+        if ine is None or link.get("name") not in m.frame_names:
+            continue
+        org, I = ine.find("origin"), ine.find("inertia")
+        xyz = [float(v) for v in ((org.get("xyz") if org is not None else None) or "0 0 0").split()]
+        rpy = [float(v) for v in ((org.get("rpy") if org is not None else None) or "0 0 0").split()]
+        Ic = np.array([[float(I.get("ixx")), float(I.get("ixy")), float(I.get("ixz"))],
+                       [float(I.get("ixy")), float(I.get("iyy")), float(I.get("iyz"))],
+                       [float(I.get("ixz")), float(I.get("iyz")), float(I.get("izz"))]])
+        links.append((m.frame_id(link.get("name")), float(ine.find("mass").get("value")), torch.tensor(xyz, dtype=torch.float64, device="cuda"),
+                      torch.from_numpy(_rpy(*rpy) @ Ic @ _rpy(*rpy).T).cuda()))
+
+    def energy(qs, qds):
+        E = torch.zeros(U, dtype=torch.float64, device="cuda")
+        for fr, mass, xyz, Ic in links:
+            pos, rot = ev.fk(fr, qs)
+            tw = torch.einsum("rju,ju->ru", ev.jacobian(fr, qs).view(6, n, U), qds)
+            R = rot.view(3, 3, U)
+            w = tw[3:]
+            r_c = torch.einsum("iju,j->iu", R, xyz)
+            vc = tw[:3] + torch.linalg.cross(w, r_c, dim=0)
+            wl = torch.einsum("jiu,ju->iu", R, w)
+            E += 0.5 * (mass * (vc * vc).sum(0) + torch.einsum("iu,ij,ju->u", wl, Ic, wl)) + mass * 9.81 * (pos[2] + r_c[2])
+        return E
+
+    h = 1e-5
+    Ep = energy((q + h * qd + 0.5 * h * h * qdd).contiguous(), (qd + h * qdd).contiguous())
+    Em = energy((q - h * qd + 0.5 * h * h * qdd).contiguous(), (qd - h * qdd).contiguous())
+    dE = (Ep - Em) / (2 * h)
+    power = (qd * ev.rnea(q, qd, qdd)).sum(0)
+    assert float((power - dE).abs().max()) < 1e-6 * max(1.0, float(dE.abs().max()))
