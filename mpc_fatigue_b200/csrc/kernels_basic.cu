@@ -536,6 +536,10 @@ __global__ void __launch_bounds__(kThreads, 3) node_eval_chain_kernel(const __gr
         b[i] = qd ? qd[i * U + u] : 0.0;
         c[i] = qdd ? qdd[i * U + u] : 0.0;
     }
+    if (Tnext) {  // the temperatures are read after the dynamics: start their loads now (no registers held)
+#pragma unroll
+        for (int i = 0; i < N; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(T + i * U + u));
+    }
     WrenchExt<N, NEE> ext;
     ext.wsign = wsign;
 #pragma unroll
