@@ -71,7 +71,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
+    def wait_first(self, timeout: float = 10.0):
+        """nvidia-smi needs a second or more before its first line on a fresh box: do not enter the timed region before."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self) -> int:
+        return len(self.rows)
+
+    def stop(self, i0: int = 0, i1: int | None = None) -> dict:
+        """Statistics over the samples rows[i0:i1] (the timed region); if none fell inside it (a very short region), over
+        everything sampled since start(), i.e. warm-up + timed steps of the same kernels, and says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -81,7 +92,11 @@ class ClockSampler:
             self.proc.kill()
         mhz, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = "timed region"
+        rows = self.rows[i0:i1]
+        if not rows:
+            rows, window = self.rows, "warm-up + timed region (no sample fell inside the timed region)"
+        for r in rows:
             if len(r) < 6:
                 continue
             try:
@@ -94,7 +109,7 @@ class ClockSampler:
                     reasons.add(nm)
         mhz.sort()
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz)}
+                "samples": len(mhz), "window": window}
 
 
 def measured_peaks() -> dict:
@@ -239,23 +254,26 @@ def run_gpu(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    fence()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    fence()
+    if rank == 0:
+        sampler.wait_first()
     launches0 = _capi.lib.mpcf_launch_count()
     pairs = []
     _capi.lib.mpcf_profile_enable(1)  # per-kernel CUDA events on the launch stream (read after the timed region)
     fence()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mark0 = sampler.mark()
     t0.record()
     for _ in range(args.steps):
         gathered = step(pairs)
     t1.record()
     fence()
+    mark1 = sampler.mark()
     launches = _capi.lib.mpcf_launch_count() - launches0
     el_ms = t0.elapsed_time(t1)
     ms3 = (C.c_double * 3)()
@@ -263,7 +281,7 @@ def run_gpu(args) -> None:
     _capi.lib.mpcf_profile_read(ms3, C.byref(nprof))
     _capi.lib.mpcf_profile_enable(0)
     kern = {"step_stages": ms3[0] / args.steps, "stage_derivs": ms3[1] / args.steps, "chain_rule": ms3[2] / args.steps}
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, mark1) if rank == 0 else None
     if world > 1:
         tt = torch.tensor([el_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -387,7 +405,7 @@ def run_gpu(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
