@@ -53,63 +53,81 @@ def workload_config(n_gpus: int) -> dict:
 
 # ---- clocks sampler (B200_PROFILING.md recipe) ----
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and clock-event reasons of one GPU, sampled every 50 ms by a thread through NVML (what nvidia-smi itself
+    reads; no subprocess, so no start-up delay and no pipe buffering: every sample carries its own time stamp).  Falls back
+    to one `nvidia-smi --query-gpu` call per sample when the NVML python module is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.thread, self.stop_flag, self.src = index, [], None, threading.Event(), None
+
+    def _nvml_reader(self):
+        import pynvml
+        pynvml.nvmlInit()
+        import torch
+        p = torch.cuda.get_device_properties(self.index)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)).encode())
+        mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+
+        def read():
+            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, [bool(r & b) for b in bits]
+        return read
+
+    def _smi_reader(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+        def read():
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            return float(out[0]), float(out[1]), [c.strip().lower().startswith("active") for c in out[2:6]]
+        return read
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def wait_first(self, timeout: float = 10.0):
-        """nvidia-smi needs a second or more before its first line on a fresh box: do not enter the timed region before."""
-        t0 = time.perf_counter()
-        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
-            time.sleep(0.05)
-
-    def mark(self) -> int:
-        return len(self.rows)
-
-    def stop(self, i0: int = 0, i1: int | None = None) -> dict:
-        """Statistics over the samples rows[i0:i1] (the timed region); if none fell inside it (a very short region), over
-        everything sampled since start(), i.e. warm-up + timed steps of the same kernels, and says so."""
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        mhz, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        window = "timed region"
-        rows = self.rows[i0:i1]
-        if not rows:
-            rows, window = self.rows, "warm-up + timed region (no sample fell inside the timed region)"
-        for r in rows:
-            if len(r) < 6:
-                continue
+        read = None
+        for name, make in (("nvml", self._nvml_reader), ("nvidia-smi", self._smi_reader)):
             try:
-                mhz.append(float(r[0]))
-                mx = float(r[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        mhz.sort()
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(mhz), "window": window}
+                read = make()
+                read()
+                self.src = name
+                break
+            except Exception:  # noqa: BLE001 - any failure of one source just selects the next
+                read = None
+        if read is None:
+            return
+
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    self.rows.append((time.perf_counter(),) + read())
+                except Exception:  # noqa: BLE001
+                    pass
+                self.stop_flag.wait(0.05)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    @staticmethod
+    def mark() -> float:
+        return time.perf_counter()
+
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Statistics over the samples taken inside [t0, t1] (the timed region); if none fell inside it (a very short
+        region), over everything sampled since start(), i.e. warm-up + timed steps of the same kernels, and says so."""
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable (no NVML module, no nvidia-smi)"], "samples": 0}
+        self.stop_flag.set()
+        self.thread.join(timeout=15)
+        rows = [r for r in self.rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        window = "timed region"
+        if not rows:
+            rows, window = list(self.rows), "warm-up + timed region (no sample fell inside the timed region)"
+        mhz = sorted(r[1] for r in rows)
+        reasons = sorted({nm for r in rows for nm, on in zip(self.NAMES, r[3]) if on})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": rows[-1][2] if rows else None, "reasons": reasons,
+                "samples": len(mhz), "window": window, "source": self.src}
 
 
 def measured_peaks() -> dict:
@@ -260,8 +278,6 @@ def run_gpu(args) -> None:
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
-    if rank == 0:
-        sampler.wait_first()
     launches0 = _capi.lib.mpcf_launch_count()
     pairs = []
     _capi.lib.mpcf_profile_enable(1)  # per-kernel CUDA events on the launch stream (read after the timed region)
