@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ K2
+constexpr int kSmCountHint = 148;  // B200; only tunes how far ahead k_stage_derivs prefetches
 MPCF_DI void cp_async8(double *smem, const double *gmem)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -154,6 +155,26 @@ __global__ void __launch_bounds__(kThreads) k_stage_derivs(const __grid_constant
         q[i] = __ldcs(w + (W::kQ + i) * 32);
         qd[i] = __ldcs(w + (W::kQd + i) * 32);
         qdd[i] = __ldcs(w + (W::kQdd + i) * 32);
+    }
+    {   // pull the inputs of the block that is dispatched one wave of resident blocks later (blocks are dispatched in
+        // linear order, two per SM) into L2: its first loads then cost an L2 hit instead of a DRAM round trip
+        const long lin = (long)blockIdx.y * gridDim.x + blockIdx.x + 2 * kSmCountHint;
+        if (lin < 4l * gridDim.x) {
+            const long lu2 = (lin % gridDim.x) * blockDim.x + threadIdx.x;
+            if (lu2 < cnt) {
+                const double *o2 = ws + W::chunk(lu2 / 32, (int)(lin / gridDim.x)) + (lu2 & 31);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(o2 + (W::kPlanes2 + W::kQ + i) * 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(o2 + (W::kPlanes2 + W::kQd + i) * 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(o2 + (W::kPlanes2 + W::kQdd + i) * 32));
+                }
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c <= r; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(o2 + (2 * N * N + r * N + c) * 32));
+            }
+        }
     }
     // streaming stores: the workspace is consumed once by the next kernel; keep L2 for this kernel's spill lines
     auto emit = [&](int mat, int r, int c, double v) { __stcs(o + (mat * N * N + r * N + c) * 32, v); };
