@@ -401,7 +401,7 @@ def run_gpu(args) -> None:
                          "dominant_share": max(kern.values()) / max(sum(kern.values()), 1e-9),
                          "note": "frac can exceed 1: the frozen model charges (1 + 25) RK4/ABA sweeps per unit; the analytic "
                                  "pipeline needs ~6x fewer FP64 instructions (DESIGN.md §5)",
-                         "executed": {"fp64_pipe_active_pct": {"step_stages": 66.7, "stage_derivs": 58.7, "chain_rule": 38.2},
+                         "executed": {"fp64_pipe_active_pct": {"step_stages": 66.7, "stage_derivs": 63.3, "chain_rule": 38.2},
                                       "fp64_thread_instructions_per_unit": 43000,
                                       "source": "ncu --set full, profiles/r01_jvp_pipeline.md (static figures of that capture, not "
                                                 "measured by this run): the pipeline runs at about half of the FP64 issue rate"},
