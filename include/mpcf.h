@@ -28,7 +28,9 @@
  *   - every function returns 0 on success or a negative MPCF_E* code and never throws across the ABI;
  *     mpcf_last_error() returns a thread-local message for the last failure;
  *   - a model handle is immutable after creation apart from the two explicit setters, is owned by the
- *     caller (create/destroy), and may be shared between streams.
+ *     caller (create/destroy), and may be shared between streams and host threads.  The setters are the exception:
+ *     the caller must not run them concurrently with launches on the same handle (they re-upload the constants after a
+ *     cudaDeviceSynchronize, so work already queued finishes with the old values).  One handle per device.
  */
 #ifndef MPCF_H
 #define MPCF_H
@@ -80,7 +82,8 @@ int mpcf_frame_id(const mpcf_model *model, const char *name);          /* >= 0, 
 const char *mpcf_joint_name(const mpcf_model *model, int joint);       /* NULL if out of range */
 const char *mpcf_frame_name(const mpcf_model *model, int frame);
 /* Copy a model array to host memory (tests, input generation).  field is one of:
-   "parent" "jtype" "fparent" (int32) | "Rp" "pp" "mass" "mc" "Io" "arm" "fat" "fR" "fp"
+   "parent" "jtype" "fparent" "jcontinuous" (int32; jcontinuous[i] = 1 for URDF `continuous` joints, which this library
+   parametrises by the plain angle, nq = nv = 1, where Pinocchio uses (cos, sin), nq = 2) | "Rp" "pp" "mass" "mc" "Io" "arm" "fat" "fR" "fp"
    "q_lo" "q_hi" "v_max" "tau_max" "grav" (fp64).  Returns bytes written or a negative code. */
 long mpcf_model_export(const mpcf_model *model, const char *field, void *out, size_t cap_bytes);
 int mpcf_model_set_armature(mpcf_model *model, const double *arm /* [n] host */);
@@ -128,20 +131,28 @@ int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double 
                            const double *f0, const double *tau, double dt, double *qt, double *qdt, double *ft,
                            void *stream);
 /* Same plus the dense forward-mode Jacobian jac[3n][4n+1][U]:
-   rows (q+, qd+, f+), columns (q, qd, tau, f, dt).  qn/qdn/fn may be NULL. */
+   rows (q+, qd+, f+), columns (q, qd, tau, f, dt).  qn/qdn/fn may be NULL.
+   Compile-time families ("chain3", "chain6", "chain7", "forest12x6", "forest14x7") run the analytic pipeline (forward-dynamics
+   derivatives per RK4 stage + a chain rule through the stages) staged through a device workspace that this entry takes from
+   the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on `stream`: no synchronisation, and the pool
+   keeps the block between calls).  Run-time-topology families run 3n + 1 dual-number sweeps. */
 int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,
                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                             double *qdn, double *fn, double *jac, void *stream);
-/* Faster Jacobian path for the compile-time families ("chain3", "chain6", "chain7", "forest12x6", "forest14x7"): analytic forward-dynamics
-   derivatives per RK4 stage + a chain rule through the stages, staged through a caller-owned DEVICE workspace.
-   mpcf_step_rk4_jvp_workspace_bytes() returns the size to allocate (bounded: units are processed in chunks),
-   or 0 when the model has no workspace path.  With workspace == NULL (or too small, or such a model) the call
-   falls back to the direct kernel of mpcf_step_rk4_jvp_batch; results agree to rounding. */
+/* Same with a caller-owned DEVICE workspace (one per stream): mpcf_step_rk4_jvp_workspace_bytes() returns the size to
+   allocate (bounded: units are processed in chunks of 2^20), or 0 when the model has no workspace path (then `workspace`
+   is ignored).  `workspace` must be 128-byte aligned (it is read with cp.async.bulk) and at least 32 units large; a
+   misaligned or too small non-NULL workspace is MPCF_EINVAL.  workspace == NULL behaves like mpcf_step_rk4_jvp_batch. */
 size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, long U);
 int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q, const double *qd,
                                const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                                double *qdn, double *fn, double *jac, void *workspace, size_t workspace_bytes,
                                void *stream);
+/* The same result by 3n + 1 dual-number sweeps of the RK4 step for EVERY family: an independent cross-check of the analytic
+   pipeline (results agree to rounding; ~15x slower on the compile-time families). */
+int mpcf_step_rk4_jvp_dual_batch(const mpcf_model *model, long U, const double *q, const double *qd,
+                                 const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                                 double *qdn, double *fn, double *jac, void *stream);
 /* Forward-dynamics derivatives at (q, qd, tau): A = d qdd/d q, B = d qdd/d qd, C = M^-1 = d qdd/d tau,
    each [n*n][U] with plane index row*n + col. */
 int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,

@@ -205,6 +205,7 @@ extern "C" long mpcf_model_export(const mpcf_model *m, const char *field, void *
     if (f == "parent") iv(h.parent);
     else if (f == "jtype") iv(h.jtype);
     else if (f == "fparent") iv(h.fparent);
+    else if (f == "jcontinuous") iv(h.jcontinuous);
     else if (f == "Rp") dv(h.Rp);
     else if (f == "pp") dv(h.pp);
     else if (f == "mass") dv(h.mass);
@@ -283,6 +284,11 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
             if (h.parent[j] >= 0 && h.parent[j] != j - 1) keep[h.parent[j]] = 1;
         ii.insert(ii.end(), keep.begin(), keep.end());
         cudaError_t e;
+        // a setter re-dirtied an uploaded model: kernels queued on any stream may still read the old blob
+        if (m->d_dbl && m->device == dev) cudaDeviceSynchronize();
+        if (m->d_dbl && m->device != dev) {  // first use on another device: the old buffers belong to m->device
+            return fail(MPCF_EINVAL, "model constants were uploaded to device " + std::to_string(m->device) + "; create one model handle per device");
+        }
         if (!m->d_dbl && (e = cudaMalloc(&m->d_dbl, d.size() * sizeof(double))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");
         if (!m->d_int && (e = cudaMalloc(&m->d_int, ii.size() * sizeof(int))) != cudaSuccess) return cuda_fail(e, "cudaMalloc(model)");
         // synchronous copies: the model is immutable afterwards and may be used from any stream
@@ -296,11 +302,14 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
     return MPCF_OK;
 }
 
-// Forward dynamics needs D_i = S_i^T IA_i S_i + armature_i > 0.  IA_i >= the composite rigid inertia of the
-// subtree, so check the composite inertia about each joint axis at q = 0 once per model (host, O(n)).
+// Forward dynamics needs D_i = S_i^T IA_i S_i + armature_i > 0.  The articulated inertia IA_i is bounded ABOVE by the
+// composite rigid inertia of the subtree (IA_i <= Ic_i), so a zero composite inertia about a joint axis at q = 0 is a
+// sufficient reason to refuse (the shipped Pilz flange: mass at the joint origin, zero tensor), not a guarantee that every
+// configuration is regular: the kernels themselves turn a non-positive pivot into NaN outputs (dyn.cuh: fd_crba / aba).
 static int check_forward_dynamics(const mpcf_model *cm)
 {
     mpcf_model *m = const_cast<mpcf_model *>(cm);
+    std::lock_guard<std::mutex> lk(m->mu);
     if (m->fd_status == 0) {
         const HostModel &h = m->h;
         const int n = h.n;
@@ -452,16 +461,6 @@ extern "C" int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, co
     return done(launch_rollout(lm, B, N, q0, qd0, f0, tau, dt, qt, qdt, ft, st), "rollout_rk4_batch");
 }
 
-extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
-                                       const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
-                                       double *jac, void *stream)
-{
-    PROLOGUE(q && qd && tau && f && jac)
-    if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
-    if (int rc = check_forward_dynamics(model)) return rc;
-    return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
-}
-
 // Workspace of the analytic Jacobian pipeline: (16 n + 12 n^2) doubles per unit, processed in chunks of at most
 // 2^20 units, so the request is bounded (4.4 GB for n = 6) however large U is.
 static const long kJvpChunkUnits = 1L << 20;
@@ -477,6 +476,18 @@ extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, lon
     return (size_t)units * jvp_ws_doubles_per_unit(nchain) * sizeof(double);
 }
 
+// the dual-number sweep kernel (3n + 1 seeds): every family; the cross-check of the analytic pipeline and the path of the
+// run-time-topology families
+extern "C" int mpcf_step_rk4_jvp_dual_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                                            const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                                            double *jac, void *stream)
+{
+    PROLOGUE(q && qd && tau && f && jac)
+    if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
+    if (int rc = check_forward_dynamics(model)) return rc;
+    return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_dual_batch");
+}
+
 extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
                                           const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
                                           double *jac, void *workspace, size_t workspace_bytes, void *stream)
@@ -484,12 +495,34 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
     PROLOGUE(q && qd && tau && f && jac)
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
-    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
-    if (!jvp2_supported(lm) || !workspace || workspace_bytes < min_ws)  // no workspace path: direct dual-number kernel
+    if (!jvp2_supported(lm))  // run-time topology: no workspace pipeline; the workspace argument is ignored
         return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
-    if (reinterpret_cast<uintptr_t>(workspace) % 8) return fail(MPCF_EINVAL, "workspace must be 8-byte aligned");
-    return done(launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(workspace), workspace_bytes, st),
-                "step_rk4_jvp_ws_batch");
+    if (U == 0) return MPCF_OK;
+    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
+    if (workspace) {
+        // the chain-rule kernel streams the workspace with cp.async.bulk: 16-byte aligned global addresses; chunk offsets
+        // are multiples of 256 B, so the base decides.  128 keeps every plane on a full cache line.
+        if (reinterpret_cast<uintptr_t>(workspace) % 128) return fail(MPCF_EINVAL, "workspace must be 128-byte aligned");
+        if (workspace_bytes < min_ws) return fail(MPCF_EINVAL, "workspace too small: see mpcf_step_rk4_jvp_workspace_bytes");
+        return done(launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(workspace), workspace_bytes, st),
+                    "step_rk4_jvp_ws_batch");
+    }
+    // no caller workspace: stream-ordered allocation from the device's memory pool (no synchronisation; the pool keeps the
+    // block after the first call, so steady-state calls cost two pool look-ups)
+    const size_t bytes = mpcf_step_rk4_jvp_workspace_bytes(model, U);
+    void *ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, bytes, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(jvp workspace)");
+    e = launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(ws), bytes, st);
+    const cudaError_t e2 = cudaFreeAsync(ws, st);
+    return done(e != cudaSuccess ? e : e2, "step_rk4_jvp_batch");
+}
+
+extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
+                                       const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                                       double *jac, void *stream)
+{
+    return mpcf_step_rk4_jvp_ws_batch(model, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, nullptr, 0, stream);
 }
 
 extern "C" int mpcf_fd_derivs_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau, double *A,

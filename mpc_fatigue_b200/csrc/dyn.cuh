@@ -50,6 +50,7 @@ MPCF_DI void sincos_t(Dual q, Dual &s, Dual &c)
     s = Dual(sv, cv * q.d);
     c = Dual(cv, -sv * q.d);
 }
+MPCF_DI double nan_value() { return __longlong_as_double(0x7ff8000000000000ll); }
 MPCF_DI double value_of(double a) { return a; }
 MPCF_DI double value_of(Dual a) { return a.v; }
 MPCF_DI double tangent_of(double) { return 0.0; }
@@ -568,7 +569,7 @@ struct Dyn {
                 U[3] = I.B[6]; U[4] = I.B[7]; U[5] = I.B[8];
                 D = I.A[5] + m.arm(i);
             }
-            if (value_of(D) == 0.0) { ok = false; D = T(1.0); }
+            if (!(value_of(D) > 0.0)) { ok = false; D = T(nan_value()); }  // singular: NaN outputs, never a plausible wrong number
             const T Dinv = recip(D);
             L[i].Dinv = Dinv;
             const T u = tau[i] - pA[i][pr ? 2 : 5];
@@ -753,7 +754,7 @@ struct Dyn {
                     U[3] = I.B[6]; U[4] = I.B[7]; U[5] = I.B[8];
                     D = I.A[5] + m.arm(i);
                 }
-                if (value_of(D) == 0.0) { ok = false; D = T(1.0); }
+                if (!(value_of(D) > 0.0)) { ok = false; D = T(nan_value()); }  // singular: NaN outputs, never a plausible wrong number
                 const T Dinv = recip(D);
                 const T u = tau[i] - p[pr ? 2 : 5];
 #pragma unroll
@@ -976,7 +977,7 @@ struct Dyn {
                 T d = Mx[c0 + j][j];
 #pragma unroll
                 for (int k = 0; k < j; ++k) d -= Lm[j][k] * LD[j][k];
-                if (value_of(d) == 0.0) { ok = false; d = T(1.0); }
+                if (!(value_of(d) > 0.0)) { ok = false; d = T(nan_value()); }  // non-positive pivot of M: NaN outputs
                 Dinv[j] = recip(d);
 #pragma unroll
                 for (int i = j + 1; i < L; ++i) {

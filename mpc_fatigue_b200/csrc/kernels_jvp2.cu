@@ -17,7 +17,9 @@
 //
 // Cost per unit drops from 19 dual-number sweeps of RK4(ABA) (v1, kernels_jvp.cu) to one primal sweep, four
 // derivative evaluations and 19 cheap column recursions.  Generic (run-time tree) models keep the v1 kernel.
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "derivs.cuh"
@@ -719,26 +721,33 @@ __global__ void __launch_bounds__(32 * NCY, 2)
 // ------------------------------------------------------------------------------------------------ launchers
 // Optional per-kernel timing (bench.py roofline): when enabled, every kernel of the pipeline is bracketed by CUDA
 // events on the launch stream; jvp_profile_read() synchronises and returns the accumulated milliseconds per kernel.
+// The event list is shared by all host threads that launch while profiling is on: guarded by a mutex (taken only when
+// profiling is enabled; the flag itself is atomic).
 struct ProfEvent { cudaEvent_t a, b; int k; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfEvent> g_prof;
-void jvp_profile_enable(bool on) { g_prof_on = on; }
-static void prof_begin(int k, cudaStream_t s)
+void jvp_profile_enable(bool on) { g_prof_on.store(on); }
+// returns the event to record at the end of the bracket (nullptr when profiling is off)
+static cudaEvent_t prof_begin(int k, cudaStream_t s)
 {
-    if (!g_prof_on) return;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return nullptr;
     ProfEvent e;
     cudaEventCreate(&e.a);
     cudaEventCreate(&e.b);
     e.k = k;
     cudaEventRecord(e.a, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(e);
+    return e.b;
 }
-static void prof_end(cudaStream_t s)
+static void prof_end(cudaEvent_t b, cudaStream_t s)
 {
-    if (g_prof_on) cudaEventRecord(g_prof.back().b, s);
+    if (b) cudaEventRecord(b, s);
 }
 int jvp_profile_read(double *ms3, long *launches)
 {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     ms3[0] = ms3[1] = ms3[2] = 0.0;
     *launches = (long)g_prof.size();
     for (auto &e : g_prof) {
@@ -789,9 +798,11 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
     constexpr int kK2Slab = (18 * (N - 1) + N * (N + 1) / 2) * kK2Threads * (int)sizeof(double);
     constexpr bool kK2Smem = N == L && 2 * kK2Slab <= 227 * 1024;
     if constexpr (kTma) {
-        static bool attr_set[64] = {};  // function attributes are per device: set them once on each device a process uses
+        // function attributes are per device: set them once on each device a process uses (idempotent, so two threads
+        // racing through the first call is harmless; the flag is atomic)
+        static std::atomic<bool> attr_set[64];
         const int dev = current_device();
-        if (!attr_set[dev]) {
+        if (!attr_set[dev].load(std::memory_order_acquire)) {
             cudaError_t e = cudaSuccess;
             if constexpr (kCpwDefault == 1) {
                 e = cudaFuncSetAttribute(k_chain_rule_tma<N, L, NBUF, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -807,17 +818,17 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
                 e = cudaFuncSetAttribute(k_stage_derivs<N, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2Slab);
                 if (e != cudaSuccess) return e;
             }
-            attr_set[dev] = true;
+            attr_set[dev].store(true, std::memory_order_release);
         }
     }
     for (long u0 = 0; u0 < U; u0 += Uc) {
         const long cnt = (U - u0) < Uc ? (U - u0) : Uc;
         const unsigned gb = (unsigned)((cnt + kThreads - 1) / kThreads);
         const long ntiles = (cnt + 31) / 32;
-        prof_begin(0, s);
+        cudaEvent_t pe = prof_begin(0, s);
         k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
-        prof_end(s);
-        prof_begin(1, s);
+        prof_end(pe, s);
+        pe = prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
         bool k2done = false;
         if constexpr (kK2Smem) {
@@ -827,8 +838,8 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
             }
         }
         if (!k2done) k_stage_derivs<N, L, false><<<dim3(gb, 4), kThreads, 0, s>>>(P, cnt, ws);
-        prof_end(s);
-        prof_begin(2, s);
+        prof_end(pe, s);
+        pe = prof_begin(2, s);
         if constexpr (kTma) {
             const unsigned g3 = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
             static const int cpw_env = getenv("MPCF_K3_CPW") ? atoi(getenv("MPCF_K3_CPW")) : 1;
@@ -843,7 +854,7 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
         } else {
             k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
         }
-        prof_end(s);
+        prof_end(pe, s);
         g_launches.fetch_add(3);
     }
     return cudaGetLastError();

@@ -206,6 +206,7 @@ int HostModel::add_joint(int parent_joint, int type, const std::string &name, co
     int idx = n++;
     parent.push_back(parent_joint);
     jtype.push_back(type);
+    jcontinuous.push_back(0);
     joint_names.push_back(name);
     Rp.insert(Rp.end(), R, R + 9);
     pp.insert(pp.end(), p, p + 3);
@@ -292,12 +293,13 @@ struct UrdfCtx {
             const XmlNode *ax = je->child("axis");
             double a[3];
             if (!parse_floats(ax ? ax->get("xyz") : nullptr, 3, a, 0.0)) { err = "bad <axis> in joint " + jname; code = MPCF_EPARSE; return false; }
-            if (!ax) { a[0] = 1; a[1] = 0; a[2] = 0; }  // URDF default axis
+            if (!ax || !ax->get("xyz")) { a[0] = 1; a[1] = 0; a[2] = 0; }  // URDF default axis (element or attribute missing)
             if (a[0] == 0 && a[1] == 0 && a[2] == 0) { err = "zero <axis> in joint " + jname; code = MPCF_EPARSE; return false; }
             double Ra[9], Rn[9], RaT[9];
             axis_to_R(a, Ra);
             mat_mul(Rj, Ra, Rn);
             int idx = mdl->add_joint(jidx, jt, jname, Rn, pj, *opts);
+            mdl->jcontinuous[idx] = type == "continuous";
             if (const XmlNode *lim = je->child("limit")) {
                 parse_float(lim->get("lower"), &mdl->q_lo[idx], -M_PI);
                 parse_float(lim->get("upper"), &mdl->q_hi[idx], M_PI);
@@ -305,8 +307,11 @@ struct UrdfCtx {
                 parse_float(lim->get("effort"), &mdl->tau_max[idx], 1.0);
             }
             const double zero[3] = {0, 0, 0};
-            mdl->add_frame(jname, idx, kEye, zero);
+            // The joint's own frame keeps the URDF (un-normalised) orientation, as Pinocchio's JOINT frame does: its pose is
+            // Rj * Rot(axis, q) = (Rj Ra) Rz(q) Ra^T, i.e. Ra^T relative to the axis-normalised joint frame (identity when the
+            // axis is +z, as in every shipped Pilz URDF).
             transpose(Ra, RaT);
+            mdl->add_frame(jname, idx, RaT, zero);
             if (!visit(child, idx, RaT, zero, depth + 1)) return false;
         }
         return true;

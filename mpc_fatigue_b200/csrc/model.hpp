@@ -15,6 +15,7 @@ namespace mpcf {
 struct HostModel {
     int n = 0;
     std::vector<int> parent, jtype;          // [n]
+    std::vector<int> jcontinuous;            // [n] 1 = URDF `continuous` joint (Pinocchio: nq = 2 (cos, sin); here: plain angle)
     std::vector<std::string> joint_names;    // [n]
     std::vector<double> Rp, pp;              // [n][9], [n][3]   joint placement in the parent joint frame
     std::vector<double> mass, mc, Io;        // [n], [n][3], [n][6]  (Io about the joint origin)

@@ -203,14 +203,21 @@ class BatchEvaluator:
 
     def step_rk4_jvp(self, q, qd, tau, f, dt, out=None, jac=None, direct: bool = False):
         """Step plus dense forward-mode Jacobian jac[3n, 4n+1, U]: rows (q+,qd+,f+), cols (q,qd,tau,f,dt).
-        Chain models use the analytic workspace pipeline; `direct=True` forces the dual-number kernel."""
+        Chain models use the analytic workspace pipeline (the evaluator keeps one workspace per instance, i.e. per stream
+        of use); `direct=True` runs the 3n + 1 dual-number sweeps instead (cross-check)."""
         U, n = self._U(q), self.n
         qn, qdn, fn = out if out is not None else (None, None, None)
         qn, qdn, fn = self._out(qn, n, U, "qn"), self._out(qdn, n, U, "qdn"), self._out(fn, n, U, "fn")
         jac = self._out(jac, (3 * n, 4 * n + 1), U, "jac")
         dts, dtu = self._dt(dt, U)
         with torch.cuda.device(self.device):
-            ws, ws_bytes = (None, 0) if direct else self._workspace(U)
+            if direct:
+                _capi.check(_capi.lib.mpcf_step_rk4_jvp_dual_batch(
+                    self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(tau, n, U, "tau"),
+                    self._in(f, n, U, "f"), dts, dtu, C.c_void_p(qn.data_ptr()), C.c_void_p(qdn.data_ptr()),
+                    C.c_void_p(fn.data_ptr()), C.c_void_p(jac.data_ptr()), _stream()))
+                return qn, qdn, fn, jac
+            ws, ws_bytes = self._workspace(U)
             _capi.check(_capi.lib.mpcf_step_rk4_jvp_ws_batch(
                 self.model.handle, U, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(tau, n, U, "tau"),
                 self._in(f, n, U, "f"), dts, dtu, C.c_void_p(qn.data_ptr()), C.c_void_p(qdn.data_ptr()),

@@ -182,7 +182,7 @@ def load_urdf(xml_text: str, armature: float = 0.0, ktau: float | list[float] = 
             if jt not in ("revolute", "continuous", "prismatic"):
                 raise ValueError("unsupported joint type %r (joint %s)" % (jt, je.get("name")))
             ax = je.find("axis")
-            a = _floats(ax.get("xyz") if ax is not None else "1 0 0", 3)
+            a = _floats(ax.get("xyz") if ax is not None and ax.get("xyz") is not None else "1 0 0", 3)
             Ra = axis_to_R(a)
             lim = je.find("limit")
             idx = mdl.n
@@ -203,7 +203,8 @@ def load_urdf(xml_text: str, armature: float = 0.0, ktau: float | list[float] = 
             mdl.q_hi.append(g("upper", math.pi))
             mdl.v_max.append(g("velocity", 1.0))
             mdl.tau_max.append(g("effort", 1.0))
-            add_frame(je.get("name"), idx, np.eye(3), np.zeros(3))
+            # the joint's own frame keeps the URDF orientation (Pinocchio JOINT frame): Ra^T in the axis-normalised joint frame
+            add_frame(je.get("name"), idx, Ra.T.copy(), np.zeros(3))
             visit(child, idx, Ra.T.copy(), np.zeros(3))
 
     visit(roots[0], -1, np.eye(3), np.zeros(3))

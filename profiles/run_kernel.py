@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Profiling driver: launches one hot-path kernel a few times on the C2 workload shape (smaller B by default).
-    python profiles/run_kernel.py jvp|step|rnea|node [B] [reps]
+    python profiles/run_kernel.py jvp|step|rnea|node [B] [reps] [pilz6|pilz6x2|humanoid37] [N]
 Used under ncu (see profiles/README.md); never a source of bench numbers."""
 import os
 import sys
@@ -15,17 +15,19 @@ from mpc_fatigue_b200.synth import synth_batch
 which = sys.argv[1] if len(sys.argv) > 1 else "jvp"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-N, dt = 100, 0.02
+mname = sys.argv[4] if len(sys.argv) > 4 else "pilz6"
+N = int(sys.argv[5]) if len(sys.argv) > 5 else 100
+dt = 0.02
 dev = torch.device("cuda", 0)
-m = Model.from_urdf(data_urdf("pilz6"), armature=1e-2)
+m = Model.synthetic("humanoid", 37, seed=7, armature=1e-2) if mname == "humanoid37" else Model.from_urdf(data_urdf(mname), armature=1e-2)
 ev = BatchEvaluator(m, dev)
 lim = {k: m.export(k) for k in ("q_lo", "q_hi", "v_max", "tau_max")}
 q, qd, tau, f = synth_batch(lim, 0, B, N, device=dev)
 U = B * N
 out = tuple(torch.empty_like(q) for _ in range(3))
-jac = torch.empty((18, 25, U), dtype=torch.float64, device=dev) if which == "jvp" else None
+jac = torch.empty((3 * m.n, 4 * m.n + 1, U), dtype=torch.float64, device=dev) if which == "jvp" else None
 W = torch.zeros((6, U), dtype=torch.float64, device=dev)
-fr = m.frame_id("prbt_link_5")
+fr = m.frame_id("prbt_link_5") if mname == "pilz6" else m.nframes - 1
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for r in range(reps + 1):
     if r == 1:

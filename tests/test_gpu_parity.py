@@ -296,10 +296,23 @@ def test_workspace_smaller_than_batch_is_chunked():
     assert _capi.lib.mpcf_launch_count() - launches0 == 3 * 5
     torch.cuda.synchronize()
     assert torch.equal(jac, ref[3]) and all(torch.equal(a, b) for a, b in zip(out, ref[:3]))
-    # a workspace below one 32-unit tile falls back to the direct kernel (results agree to rounding)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # a non-NULL workspace below one 32-unit tile, or a misaligned one, is an error (never a silent slow path)
     rc = _capi.lib.mpcf_step_rk4_jvp_ws_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]),
-                                              p(jac), p(ws), 1024, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    _capi.check(rc)
+                                              p(jac), p(ws), 1024, st)
+    assert rc == _capi.EINVAL and "too small" in _capi.last_error()
+    rc = _capi.lib.mpcf_step_rk4_jvp_ws_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]),
+                                              p(jac), C.c_void_p(ws.data_ptr() + 8), need64 - 8, st)
+    assert rc == _capi.EINVAL and "aligned" in _capi.last_error()
+    # the header-default entry (no workspace argument) runs the same pipeline on a pool-allocated workspace: bit-identical
+    jac.zero_()
+    launches0 = _capi.lib.mpcf_launch_count()
+    _capi.check(_capi.lib.mpcf_step_rk4_jvp_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]), p(jac), st))
+    assert _capi.lib.mpcf_launch_count() - launches0 == 3
+    torch.cuda.synchronize()
+    assert torch.equal(jac, ref[3])
+    # the dual-number sweeps agree to rounding
+    _capi.check(_capi.lib.mpcf_step_rk4_jvp_dual_batch(m.handle, U, p(q), p(qd), p(tau), p(f), 0.02, None, p(out[0]), p(out[1]), p(out[2]), p(jac), st))
     assert float((jac - ref[3]).abs().max() / ref[3].abs().max()) < 1e-11
 
 

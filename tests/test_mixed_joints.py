@@ -198,3 +198,61 @@ def test_gpu_power_balance_at_scale():
     dE = (Ep - Em) / (2 * h)
     power = (qd * ev.rnea(q, qd, qdd)).sum(0)
     assert float((power - dE).abs().max()) < 1e-6 * max(1.0, float(dE.abs().max()))
+
+
+# ---- joint frames keep the URDF orientation (model.cpp / urdf_model.py registered them as identity) ----
+def _rodrigues(axis, ang):
+    a = np.asarray(axis, dtype=float) / np.linalg.norm(axis)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+
+def _rpy(r, p, y):
+    return _rodrigues([0, 0, 1], y) @ _rodrigues([0, 1, 0], p) @ _rodrigues([1, 0, 0], r)
+
+
+def _hand_joint_frames(q):
+    """World pose of the JOINT frames `slide`, `swing`, `spin` of mixed_joints.urdf written out by hand from the URDF text
+    (Pinocchio semantics: joint frame = parent placement * <origin> * motion about the URDF <axis>; no axis normalisation)."""
+    R0, p0 = _rpy(0, 0.3, 0), np.array([0.0, 0.0, 0.2])
+    p_slide = p0 + R0 @ (q[0] * np.array([1.0, 0.0, 0.0]))       # prismatic along x: orientation unchanged
+    R_swing = R0 @ _rpy(0.2, 0, -0.4) @ _rodrigues([0, 1, 0], q[1])
+    p_swing = p_slide + R0 @ np.array([0.1, 0.0, 0.1])
+    R_spin = R0 @ _rpy(1.2, 0, 0) @ _rodrigues([0.6, 0, 0.8], q[2])
+    p_spin = p_slide + R0 @ np.array([-0.1, 0.05, 0.0])
+    return {"slide": (R0, p_slide), "swing": (R_swing, p_swing), "spin": (R_spin, p_spin)}
+
+
+def test_joint_frames_keep_the_urdf_orientation():
+    om = load_urdf(XML, armature=0.0)
+    orc = Oracle(om)
+    m = Model.from_urdf(XML)
+    # both loaders register the joint frames with Ra^T, and agree
+    assert np.abs(m.export("fR").reshape(-1) - om.arrays()["fR"].reshape(-1)).max() < 1e-15
+    rng = np.random.default_rng(11)
+    q = np.ascontiguousarray(rng.uniform(-1.0, 1.0, (3, 7)))
+    for name in ("slide", "swing", "spin"):
+        # the joint frame is the second frame of that name? no: link frames carry link names; joint names are unique here
+        fid = om.frame_names.index(name)
+        pos, rot = orc.fk(fid, q)
+        for u in range(q.shape[1]):
+            R, p = _hand_joint_frames(q[:, u])[name]
+            assert np.abs(rot[:, u].reshape(3, 3) - R).max() < 1e-13, name
+            assert np.abs(pos[:, u] - p).max() < 1e-13, name
+
+
+@pytest.mark.gpu
+def test_gpu_joint_frames_keep_the_urdf_orientation():
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    m = Model.from_urdf(XML)
+    ev = BatchEvaluator(m)
+    rng = np.random.default_rng(12)
+    q = np.ascontiguousarray(rng.uniform(-1.0, 1.0, (3, 33)))
+    dq = torch.from_numpy(q).cuda()
+    for name in ("slide", "swing", "spin"):
+        pos, rot = ev.fk(m.frame_id(name), dq)
+        pos, rot = pos.cpu().numpy(), rot.cpu().numpy()
+        for u in range(q.shape[1]):
+            R, p = _hand_joint_frames(q[:, u])[name]
+            assert np.abs(rot[:, u].reshape(3, 3) - R).max() < 1e-13 and np.abs(pos[:, u] - p).max() < 1e-13, name
