@@ -88,6 +88,18 @@ const char *mpcf_frame_name(const mpcf_model *model, int frame);
 long mpcf_model_export(const mpcf_model *model, const char *field, void *out, size_t cap_bytes);
 int mpcf_model_set_armature(mpcf_model *model, const double *arm /* [n] host */);
 int mpcf_model_set_fatigue(mpcf_model *model, const double *rows /* [n][4] host: lambda kappa ctau cv */);
+/* Coupled fatigue of a two-arm model carrying one box (config C3 "dual-arm with coupled fatigue states"; builder-defined, the
+   reference only has the box equilibrium F_L,z + F_R,z = m g, python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:197,272-274).  Zero-order
+   hold over the step: arm c carries the share s_c = Phi_other / (Phi_0 + Phi_1) of the box weight (Phi_c = sum of the arm's
+   fatigue states at the start of the step), and its windings heat with theat_i = tau_i + s_c [J_ee,c(q)^T (0,0,weight,0,0,0)]_i
+   while the dynamics keep tau.  mpcf_step_rk4_batch and the three analytic mpcf_step_rk4_jvp*_batch entries then evaluate the
+   coupled step and its Jacobian (d f+/d f becomes a dense cross-arm block, d f+/d q gains the load term).  Two-arm families
+   only (forest12x6, forest14x7); ee_frame[c] must be carried by arm c.  NULL removes the coupling. */
+typedef struct {
+    int ee_frame[2];
+    double weight; /* m g of the box, e.g. 30 * 9.81 (Box_Pilz_6DOF2.py:197) */
+} mpcf_coupling;
+int mpcf_model_set_coupling(mpcf_model *model, const mpcf_coupling *coupling);
 /* name of the kernel family a model dispatches to: "chain3", "chain6", "chain7", "forest12x6", "forest14x7" (compile-time
  * topologies: serial revolute chains and forests of two of them) or "generic16" / "generic64" (run-time topology) */
 const char *mpcf_model_kernel_family(const mpcf_model *model);
@@ -148,6 +160,14 @@ int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const double *q,
                                const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                                double *qdn, double *fn, double *jac, void *workspace, size_t workspace_bytes,
                                void *stream);
+/* Unit-range form of the same call: evaluates `cnt` units whose input / state planes have stride `ld` (pass base pointers
+   shifted to the first unit of the range) and writes the Jacobian into a buffer of plane stride `ld_jac` >= cnt,
+   jac[3n][4n+1][ld_jac].  A caller sweeps a batch larger than the Jacobian memory it owns by reusing one chunk-sized
+   Jacobian buffer (config C5).  Needs a caller workspace for the compile-time families. */
+int mpcf_step_rk4_jvp_strided_batch(const mpcf_model *model, long cnt, long ld, const double *q, const double *qd,
+                                    const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                                    double *qdn, double *fn, double *jac, long ld_jac, void *workspace,
+                                    size_t workspace_bytes, void *stream);
 /* The same result by 3n + 1 dual-number sweeps of the RK4 step for EVERY family: an independent cross-check of the analytic
    pipeline (results agree to rounding; ~15x slower on the compile-time families). */
 int mpcf_step_rk4_jvp_dual_batch(const mpcf_model *model, long U, const double *q, const double *qd,
@@ -178,6 +198,18 @@ int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, const doubl
                              const double *fn, double dt, double w_qd, double w_tau, double tau0,
                              double alpha, double tau_floor, double f_max, double *out, void *stream);
 
+/* Same reduction with the torque limits given as a DEVICE table bound_table[N][n][2] = (lb, ub) per node and joint, which
+   covers the reference's three torque-limit mechanisms: F0 decaying bound (force_optimization_pilz_6DOF.py:136-148), F2
+   stepwise bounds over segments of the horizon (both_robots_torque_limited_2_pilz.py:129-147, Box_Pilz_6DOF2.py:303-433) and
+   F3 joint switch-off |tau_i| <= C_i after the first third for the joints selected by S (Centauro_dynamics.py:327-348).
+     resid[1][b] = max_k max_i max(lb_ki - tau_ki, tau_ki - ub_ki, 0)
+   out has row stride ld_out >= B (0 = B): a scenario chunk can write its columns of a larger [4][B_total] send buffer.
+   2 n N doubles must fit 200 KB of shared memory (MPCF_ELIMIT otherwise). */
+int mpcf_cost_residual_table_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd,
+                                   const double *f, const double *tau, const double *qn, const double *qdn,
+                                   const double *fn, double w_qd, double w_tau, const double *bound_table,
+                                   double f_max, double *out, long ld_out, void *stream);
+
 /* FP64-pipe probe for the roofline denominator: every thread of `blocks` x 256 runs 8 independent DFMA
    chains for `iters` iterations and writes one double to out[blocks*256] (device).
    flops = blocks * 256 * iters * 16.  Time it with events on `stream`. */
@@ -188,6 +220,12 @@ int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream);
    scenario-chunk slice of every SoA plane in one DMA. */
 int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
                         size_t height, int kind, void *stream);
+
+/* dst[k][u] = src[plane_map[k]][u] for k < nplanes, u < U (src planes have stride ld_src >= U; plane_map is a DEVICE int32
+   array; src and dst 16-byte aligned): packs the planes a host consumer wants (states + the structurally non-zero Jacobian
+   planes) into one contiguous device buffer, so that a scenario chunk goes back to the host in ONE copy. */
+int mpcf_gather_planes(const double *src, long ld_src, const int *plane_map, int nplanes, long U, double *dst,
+                       void *stream);
 
 /* Diagnostics: bracket each kernel of the workspace Jacobian pipeline with CUDA events on its launch stream.
    mpcf_profile_read synchronises and returns accumulated ms of (step_stages, stage_derivs, chain_rule) and the

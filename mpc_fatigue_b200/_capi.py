@@ -28,6 +28,10 @@ class Opts(C.Structure):
                 ("kappa", C.c_double), ("ctau", C.c_double), ("cv", C.c_double)]
 
 
+class Coupling(C.Structure):
+    _fields_ = [("ee_frame", C.c_int * 2), ("weight", C.c_double)]
+
+
 _dp = C.c_void_p  # device pointers travel as integers
 _sig = {
     "mpcf_opts_default": (None, [C.POINTER(Opts)]),
@@ -41,6 +45,7 @@ _sig = {
     "mpcf_model_export": (C.c_long, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]),
     "mpcf_model_set_armature": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "mpcf_model_set_fatigue": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "mpcf_model_set_coupling": (C.c_int, [C.c_void_p, C.POINTER(Coupling)]),
     "mpcf_model_kernel_family": (C.c_char_p, [C.c_void_p]),
     "mpcf_rnea_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_fk_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_long, _dp, _dp, _dp, C.c_void_p]),
@@ -57,14 +62,19 @@ _sig = {
                                           C.c_void_p]),
     "mpcf_step_rk4_jvp_dual_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp,
                                                C.c_void_p]),
+    "mpcf_step_rk4_jvp_strided_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp,
+                                                  C.c_long, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpcf_step_rk4_jvp_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_long]),
     "mpcf_step_rk4_jvp_ws_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp, _dp,
                                              C.c_void_p, C.c_size_t, C.c_void_p]),
     "mpcf_fd_derivs_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_rnea_derivs_batch": (C.c_int, [C.c_void_p, C.c_long, _dp, _dp, _dp, _dp, _dp, _dp, C.c_void_p]),
     "mpcf_cost_residual_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int] + [_dp] * 7 + [C.c_double] * 7 + [_dp, C.c_void_p]),
+    "mpcf_cost_residual_table_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int] + [_dp] * 7 + [C.c_double] * 2 + [_dp, C.c_double, _dp, C.c_long,
+                                                                                                         C.c_void_p]),
     "mpcf_probe_fp64": (C.c_int, [C.c_long, C.c_int, _dp, C.c_void_p]),
     "mpcf_memcpy2d_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
+    "mpcf_gather_planes": (C.c_int, [_dp, C.c_long, C.c_void_p, C.c_int, C.c_long, _dp, C.c_void_p]),
     "mpcf_profile_enable": (C.c_int, [C.c_int]),
     "mpcf_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "mpcf_last_error": (C.c_char_p, []),

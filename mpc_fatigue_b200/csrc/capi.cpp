@@ -28,6 +28,7 @@ struct mpcf_model {
     mutable bool dirty = true;
     mutable int device = -1;  // device holding the uploaded blob (run-time-topology families)
     int fd_status = 0;  // 0 unknown, 1 ok, -1 singular
+    CoupleHost couple;  // coupled fatigue of a two-arm model (mpcf_model_set_coupling)
 };
 
 static thread_local std::string g_err;
@@ -243,6 +244,29 @@ extern "C" int mpcf_model_set_fatigue(mpcf_model *m, const double *rows)
     return MPCF_OK;
 }
 
+extern "C" int mpcf_model_set_coupling(mpcf_model *m, const mpcf_coupling *c)
+{
+    if (!m) return fail(MPCF_EINVAL, "null model");
+    std::lock_guard<std::mutex> lk(m->mu);
+    if (!c) { m->couple = CoupleHost{}; return MPCF_OK; }
+    const int L = family_chain_len(m->fam);
+    if (family_chains(m->fam) != 2) return fail(MPCF_EINVAL, "coupled fatigue needs a two-arm model (kernel families forest12x6 / forest14x7)");
+    if (!(c->weight >= 0.0)) return fail(MPCF_EINVAL, "box weight must be >= 0");
+    CoupleHost ch;
+    ch.on = true;
+    ch.weight = c->weight;
+    for (int a = 0; a < 2; ++a) {
+        const int fr = c->ee_frame[a];
+        if (fr < 0 || fr >= (int)m->h.fparent.size()) return fail(MPCF_EFRAME, "coupling: end-effector frame index out of range");
+        const int j = m->h.fparent[fr];
+        if (j < a * L || j >= (a + 1) * L) return fail(MPCF_EFRAME, "coupling: ee_frame[" + std::to_string(a) + "] is not carried by arm " + std::to_string(a));
+        ch.ee_joint[a] = j - a * L;
+        std::memcpy(ch.ee_p[a], &m->h.fp[3 * fr], 3 * sizeof(double));
+    }
+    m->couple = ch;
+    return MPCF_OK;
+}
+
 // ---- launch plumbing ----
 static int cuda_fail(cudaError_t e, const char *what)
 {
@@ -448,7 +472,15 @@ extern "C" int mpcf_step_rk4_batch(const mpcf_model *model, long U, const double
 {
     PROLOGUE(q && qd && tau && f && qn && qdn && fn)
     if (int rc = check_forward_dynamics(model)) return rc;
-    return done(launch_step(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, st), "step_rk4_batch");
+    if (!model->couple.on || U == 0) return done(launch_step(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, st), "step_rk4_batch");
+    // coupled fatigue: heating torque from a pre-kernel into stream-ordered scratch (no synchronisation)
+    double *theat = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&theat), (size_t)model->h.n * U * sizeof(double), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(heating torque)");
+    e = launch_couple(lm, model->couple, U, U, q, f, tau, theat, U, 0, dt, dt_u, nullptr, 0, st);
+    if (e == cudaSuccess) e = launch_step(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, st, theat);
+    const cudaError_t e2 = cudaFreeAsync(theat, st);
+    return done(e != cudaSuccess ? e : e2, "step_rk4_batch (coupled)");
 }
 
 extern "C" int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double *q0, const double *qd0, const double *f0,
@@ -457,6 +489,7 @@ extern "C" int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, co
     const long U = B;
     PROLOGUE(q0 && qd0 && f0 && tau && qt && qdt && ft)
     if (N <= 0) return fail(MPCF_EINVAL, "N must be positive");
+    if (model->couple.on) return fail(MPCF_EINVAL, "the rollout entry does not support coupled fatigue: use mpcf_step_rk4_batch per step");
     if (int rc = check_forward_dynamics(model)) return rc;
     return done(launch_rollout(lm, B, N, q0, qd0, f0, tau, dt, qt, qdt, ft, st), "rollout_rk4_batch");
 }
@@ -476,6 +509,23 @@ extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, lon
     return (size_t)units * jvp_ws_doubles_per_unit(nchain) * sizeof(double);
 }
 
+// analytic pipeline on `cnt` units (plane strides ld / ld_jac), with the coupled-fatigue pre / post kernels around it when the
+// model has a coupling (heating torque in stream-ordered scratch: no synchronisation)
+static cudaError_t run_pipeline(const mpcf_model *model, const LaunchModel &lm, long cnt, long ld, const double *q, const double *qd,
+                                const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
+                                double *jac, long ld_jac, double *ws, size_t ws_bytes, cudaStream_t st)
+{
+    if (!model->couple.on) return launch_step_jvp_ws(lm, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, ws_bytes, st, cnt, ld_jac);
+    double *theat = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&theat), (size_t)model->h.n * cnt * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    e = launch_couple(lm, model->couple, cnt, ld, q, f, tau, theat, cnt, 0, dt, dt_u, nullptr, 0, st);
+    if (e == cudaSuccess) e = launch_step_jvp_ws(lm, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, ws_bytes, st, cnt, ld_jac, theat, cnt);
+    if (e == cudaSuccess) e = launch_couple(lm, model->couple, cnt, ld, q, f, tau, theat, cnt, 1, dt, dt_u, jac, ld_jac, st);
+    const cudaError_t e2 = cudaFreeAsync(theat, st);
+    return e != cudaSuccess ? e : e2;
+}
+
 // the dual-number sweep kernel (3n + 1 seeds): every family; the cross-check of the analytic pipeline and the path of the
 // run-time-topology families
 extern "C" int mpcf_step_rk4_jvp_dual_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
@@ -485,6 +535,7 @@ extern "C" int mpcf_step_rk4_jvp_dual_batch(const mpcf_model *model, long U, con
     PROLOGUE(q && qd && tau && f && jac)
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
+    if (model->couple.on) return fail(MPCF_EINVAL, "the dual-number entry does not support coupled fatigue");
     return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_dual_batch");
 }
 
@@ -504,7 +555,7 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
         // are multiples of 256 B, so the base decides.  128 keeps every plane on a full cache line.
         if (reinterpret_cast<uintptr_t>(workspace) % 128) return fail(MPCF_EINVAL, "workspace must be 128-byte aligned");
         if (workspace_bytes < min_ws) return fail(MPCF_EINVAL, "workspace too small: see mpcf_step_rk4_jvp_workspace_bytes");
-        return done(launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(workspace), workspace_bytes, st),
+        return done(run_pipeline(model, lm, U, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, U, static_cast<double *>(workspace), workspace_bytes, st),
                     "step_rk4_jvp_ws_batch");
     }
     // no caller workspace: stream-ordered allocation from the device's memory pool (no synchronisation; the pool keeps the
@@ -513,9 +564,33 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
     void *ws = nullptr;
     cudaError_t e = cudaMallocAsync(&ws, bytes, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(jvp workspace)");
-    e = launch_step_jvp_ws(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, static_cast<double *>(ws), bytes, st);
+    e = run_pipeline(model, lm, U, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, U, static_cast<double *>(ws), bytes, st);
     const cudaError_t e2 = cudaFreeAsync(ws, st);
     return done(e != cudaSuccess ? e : e2, "step_rk4_jvp_batch");
+}
+
+// Unit-range form: `cnt` units whose input / state planes have stride `ld` (base pointers already shifted to the range) and a
+// Jacobian buffer with plane stride `ld_jac` (>= cnt): lets a caller sweep a batch much larger than the Jacobian it can
+// hold by reusing one chunk-sized Jacobian buffer (config C5: 1,048,576 scenarios x 100 nodes on one GPU).
+extern "C" int mpcf_step_rk4_jvp_strided_batch(const mpcf_model *model, long cnt, long ld, const double *q, const double *qd,
+                                               const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                                               double *qdn, double *fn, double *jac, long ld_jac, void *workspace,
+                                               size_t workspace_bytes, void *stream)
+{
+    const long U = cnt;
+    PROLOGUE(q && qd && tau && f && jac)
+    if (ld < cnt || ld_jac < cnt) return fail(MPCF_EINVAL, "plane strides must be >= cnt");
+    if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
+    if (int rc = check_forward_dynamics(model)) return rc;
+    if (cnt == 0) return MPCF_OK;
+    if (!jvp2_supported(lm))
+        return done(launch_step_jvp(lm, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st, cnt, ld_jac), "step_rk4_jvp_strided_batch");
+    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
+    if (!workspace) return fail(MPCF_EINVAL, "the strided entry needs a caller workspace (mpcf_step_rk4_jvp_workspace_bytes)");
+    if (reinterpret_cast<uintptr_t>(workspace) % 128) return fail(MPCF_EINVAL, "workspace must be 128-byte aligned");
+    if (workspace_bytes < min_ws) return fail(MPCF_EINVAL, "workspace too small: see mpcf_step_rk4_jvp_workspace_bytes");
+    return done(run_pipeline(model, lm, cnt, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ld_jac, static_cast<double *>(workspace), workspace_bytes, st),
+                "step_rk4_jvp_strided_batch");
 }
 
 extern "C" int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd, const double *tau,
@@ -553,6 +628,22 @@ extern "C" int mpcf_cost_residual_batch(const mpcf_model *model, long B, int N, 
                 "cost_residual_batch");
 }
 
+extern "C" int mpcf_cost_residual_table_batch(const mpcf_model *model, long B, int N, const double *q, const double *qd, const double *f,
+                                              const double *tau, const double *qn, const double *qdn, const double *fn, double w_qd,
+                                              double w_tau, const double *bound_table, double f_max, double *out, long ld_out,
+                                              void *stream)
+{
+    if (!model) return fail(MPCF_EINVAL, "null model");
+    if (B < 0 || N <= 0) return fail(MPCF_EINVAL, "bad B / N");
+    if (ld_out <= 0) ld_out = B;
+    if (ld_out < B) return fail(MPCF_EINVAL, "ld_out must be >= B");
+    if (B > 0 && !(q && qd && f && tau && qn && qdn && fn && out && bound_table)) return fail(MPCF_EINVAL, "null array argument");
+    if ((size_t)2 * model->h.n * N * sizeof(double) > 200 * 1024) return fail(MPCF_ELIMIT, "bound table exceeds 200 KB of shared memory (2 n N doubles)");
+    return done(launch_cost_residual_table(model->h.n, B, N, q, qd, f, tau, qn, qdn, fn, w_qd, w_tau, f_max, bound_table, out, ld_out,
+                                           static_cast<cudaStream_t>(stream)),
+                "cost_residual_table_batch");
+}
+
 extern "C" int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream)
 {
     if (iters <= 0 || blocks <= 0 || !out) return fail(MPCF_EINVAL, "bad probe arguments");
@@ -570,6 +661,15 @@ extern "C" int mpcf_memcpy2d_async(void *dst, size_t dpitch, const void *src, si
     return done(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
                                   kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)),
                 "memcpy2d_async");
+}
+
+extern "C" int mpcf_gather_planes(const double *src, long ld_src, const int *plane_map, int nplanes, long U, double *dst, void *stream)
+{
+    if (nplanes < 0 || U < 0 || ld_src < U) return fail(MPCF_EINVAL, "bad sizes");
+    if (nplanes > 0 && U > 0 && !(src && plane_map && dst)) return fail(MPCF_EINVAL, "null array argument");
+    if (nplanes > 65535) return fail(MPCF_ELIMIT, "at most 65535 planes per call");
+    if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 16) return fail(MPCF_EINVAL, "src and dst must be 16-byte aligned");
+    return done(launch_gather_planes(src, dst, plane_map, nplanes, U, ld_src, static_cast<cudaStream_t>(stream)), "gather_planes");
 }
 
 // Per-kernel timing of the analytic Jacobian pipeline (diagnostics for bench.py; not thread-safe, off by default).

@@ -1036,7 +1036,8 @@ struct Dyn {
     }
 
     // xdot = (qd, FD(q, qd, tau), fatigue_rhs); x = [q | qd | f]
-    static MPCF_DI bool xdot(const MP &m, const T *x, const T *tau, T *k)
+    // theat: the torque that heats the windings; tau unless the arms' fatigue is coupled through a shared load (kernels_couple.cu)
+    static MPCF_DI bool xdot(const MP &m, const T *x, const T *tau, const T *theat, T *k)
     {
         const int n = m.n();
         constexpr int UNR = MP::kStatic ? MAXN : 1;
@@ -1044,7 +1045,7 @@ struct Dyn {
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) {
             k[i] = x[n + i];
-            k[2 * n + i] = fatigue_rhs(m, i, x[2 * n + i], tau[i], x[n + i]);
+            k[2 * n + i] = fatigue_rhs(m, i, x[2 * n + i], theat[i], x[n + i]);
         }
         return ok;
     }
@@ -1052,7 +1053,8 @@ struct Dyn {
     // classical RK4, tau held over the step.  The four stages run as a rolled loop: fully unrolled, the step kernel of a
     // 6-joint chain is 190 KB of straight-line code and spends half its time waiting for instruction fetch
     // (profiles/r01_jvp_pipeline.md); rolled, one stage body (48 KB) stays in the instruction cache.
-    static MPCF_DI bool step_rk4(const MP &m, const T *x, const T *tau, T dt, T *xn)
+    static MPCF_DI bool step_rk4(const MP &m, const T *x, const T *tau, T dt, T *xn) { return step_rk4(m, x, tau, tau, dt, xn); }
+    static MPCF_DI bool step_rk4(const MP &m, const T *x, const T *tau, const T *theat, T dt, T *xn)
     {
         const int n3 = 3 * m.n();
         constexpr int UNR3 = MP::kStatic ? 3 * MAXN : 1;
@@ -1062,7 +1064,7 @@ struct Dyn {
         bool ok = true;
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
-            ok &= xdot(m, xs, tau, k);
+            ok &= xdot(m, xs, tau, theat, k);
             const T w = dt * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
             const T c = dt * (s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0));
 #pragma unroll UNR3

@@ -71,20 +71,34 @@ cudaError_t launch_node_eval_jvp(const LaunchModel &m, const EeArgs &ee, double 
                                  const double *qdd, const double *W, double *dtau_dq, double *dtau_dqd, cudaStream_t s);
 cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *qdd, cudaStream_t s);
 cudaError_t launch_step(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
-                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s);
+                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s, const double *theat = nullptr);
+// coupled fatigue of a two-arm model (kernels_couple.cu): host-side description and the pre / post kernel
+struct CoupleHost {
+    bool on = false;
+    double weight = 0.0;
+    int ee_joint[2] = {0, 0};      // end-effector joint, local to its arm
+    double ee_p[2][3] = {{0, 0, 0}, {0, 0, 0}};
+};
+cudaError_t launch_couple(const LaunchModel &m, const CoupleHost &ch, long cnt, long ld, const double *q, const double *f, const double *tau,
+                          double *theat, long ld_t, int mode, double dt, const double *dt_u, double *jac, long UJ, cudaStream_t s);
 cudaError_t launch_rollout(const LaunchModel &m, long B, int N, const double *q0, const double *qd0, const double *f0, const double *tau,
                            double dt, double *qt, double *qdt, double *ft, cudaStream_t s);
 cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
-                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s);
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s,
+                            long cnt = -1, long UJ = 0);
 cudaError_t launch_cost_residual(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
                                  const double *qn, const double *qdn, const double *fn, const CostArgs &c, double *out,
                                  cudaStream_t s);
+cudaError_t launch_cost_residual_table(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
+                                       const double *qn, const double *qdn, const double *fn, double w_qd, double w_tau, double f_max,
+                                       const double *table, double *out, long ld_out, cudaStream_t s);
+cudaError_t launch_gather_planes(const double *src, double *dst, const int *map, int nplanes, long U, long ld_src, cudaStream_t s);
 // analytic Jacobian pipeline (kernels_jvp2.cu): static chain families, caller-provided workspace
 bool jvp2_supported(const LaunchModel &m);
 size_t jvp_ws_doubles_per_unit(int n);
 cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                                double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws,
-                               size_t ws_bytes, cudaStream_t s);
+                               size_t ws_bytes, cudaStream_t s, long cnt = -1, long UJ = 0, const double *theat = nullptr, long UT = 0);
 cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *qdd, double *Dq, double *Dv,
                                double *M, cudaStream_t s);
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,

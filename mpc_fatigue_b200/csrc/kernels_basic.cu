@@ -323,6 +323,91 @@ __global__ void __launch_bounds__(256) cost_residual_kernel(int n, long B, int N
     out[3 * B + b] = r2;
 }
 
+// Same reduction with a per-node, per-joint bound table [N][n][2] = (lb, ub) instead of the closed-form F0 schedule, which
+// covers all three torque-limit mechanisms of the reference: F0 decaying (force_optimization_pilz_6DOF.py:136-148: lb = -b_k,
+// ub = b_k), F2 stepwise over segments of the horizon (both_robots_torque_limited_2_pilz.py:129-147, Box_Pilz_6DOF2.py:303-433)
+// and F3 joint switch-off (Centauro_dynamics.py:327-348: |tau_i| <= C_i after the first third for the joints selected by S).
+// The table (2 n N doubles) is staged in shared memory once per block.  resid[1] = max violation max(lb - tau, tau - ub, 0).
+__global__ void __launch_bounds__(256) cost_residual_table_kernel(int n, long B, int N, const double *q, const double *qd, const double *f,
+                                                                const double *tau, const double *qn, const double *qdn,
+                                                                const double *fn, double w_qd, double w_tau, double f_max,
+                                                                const double *__restrict__ table, double *out, long ld_out)
+{
+    extern __shared__ double tb[];
+    for (int k = threadIdx.x; k < 2 * n * N; k += blockDim.x) tb[k] = table[k];
+    __syncthreads();
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long U = B * N;
+    double cost = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    for (int k = 0; k < N; ++k) {
+        const long u = (long)k * B + b;
+        for (int i = 0; i < n; ++i) {
+            const long o = (long)i * U + u;
+            const double v = qd[o], t = tau[o];
+            cost += w_qd * v * v + w_tau * t * t;
+            r1 = fmax(r1, fmax(tb[2 * (k * n + i)] - t, t - tb[2 * (k * n + i) + 1]));
+            r2 = fmax(r2, fn[o] - f_max);
+            if (k + 1 < N) {
+                const long o1 = o + B;
+                r0 = fmax(r0, fabs(qn[o] - q[o1]));
+                r0 = fmax(r0, fabs(qdn[o] - qd[o1]));
+                r0 = fmax(r0, fabs(fn[o] - f[o1]));
+            }
+        }
+    }
+    out[b] = cost;
+    out[ld_out + b] = r0;
+    out[2 * ld_out + b] = r1;
+    out[3 * ld_out + b] = r2;
+}
+
+cudaError_t launch_cost_residual_table(int n, long B, int N, const double *q, const double *qd, const double *f, const double *tau,
+                                       const double *qn, const double *qdn, const double *fn, double w_qd, double w_tau, double f_max,
+                                       const double *table, double *out, long ld_out, cudaStream_t s)
+{
+    if (B <= 0) return cudaSuccess;
+    const size_t smem = (size_t)2 * n * N * sizeof(double);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cost_residual_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cost_residual_table_kernel<<<(unsigned)((B + 255) / 256), 256, smem, s>>>(n, B, N, q, qd, f, tau, qn, qdn, fn, w_qd, w_tau, f_max, table, out,
+                                                                            ld_out);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// Packs selected planes of an SoA array into a contiguous staging buffer: dst[k][u] = src[map[k]][u].  The host-facing
+// pipeline uses it so that everything a chunk sends back to the host (states + the structurally non-zero Jacobian planes)
+// leaves the device in ONE large copy.  Pure HBM traffic (16-byte accesses when the plane length allows).
+__global__ void __launch_bounds__(256) gather_planes_kernel(const double *__restrict__ src, double *__restrict__ dst,
+                                                           const int *__restrict__ map, long U, long ld_src)
+{
+    const double *s = src + (size_t)map[blockIdx.y] * ld_src;
+    double *d = dst + (size_t)blockIdx.y * U;
+    const long stride = (long)gridDim.x * blockDim.x;
+    if (((U | ld_src) & 1) == 0) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(s);
+        double2 *d2 = reinterpret_cast<double2 *>(d);
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < U / 2; i += stride) __stcs(d2 + i, __ldcs(s2 + i));
+    } else {
+        for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += stride) d[i] = s[i];
+    }
+}
+
+cudaError_t launch_gather_planes(const double *src, double *dst, const int *map, int nplanes, long U, long ld_src, cudaStream_t s)
+{
+    if (nplanes <= 0 || U <= 0) return cudaSuccess;
+    long bx = (U / 2 + 255) / 256;
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    gather_planes_kernel<<<dim3((unsigned)bx, (unsigned)nplanes), 256, 0, s>>>(src, dst, map, U, ld_src);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 // FP64 pipe probe: 8 independent DFMA chains per thread; the roofline denominator of bench.py
 // (MEASURED_PEAKS.json carries no FP64 figure).  flops = blocks * threads * iters * 8 * 2.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(long iters, double *out)

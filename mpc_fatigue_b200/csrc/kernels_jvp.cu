@@ -9,8 +9,9 @@ namespace mpcf {
 // z = lambda dt (RK4 amplification of the linear compartment); the dt block writes them.
 struct StepJvpBody {
     template <class MP>
-    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, const double *f,
-                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac)
+    // cnt (the kernel wrapper's guard) units are evaluated; U is the plane stride of the input / state arrays, UJ of jac
+    static MPCF_DI void run(const MP &m, long u, long /*cnt*/, long U, long UJ, const double *q, const double *qd, const double *tau,
+                            const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac)
     {
         constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
         constexpr int UNR3 = MP::kStatic ? 3 * MP::MAXN : 1;
@@ -30,7 +31,7 @@ struct StepJvpBody {
         Dyn<Dual, MP>::step_rk4(m, x, t, h, xn);
         const long col = d < 3 * n ? d : 4 * n;
 #pragma unroll UNR3
-        for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + col) * U + u] = xn[r].d;
+        for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + col) * UJ + u] = xn[r].d;
         if (d == 0 && qn) {
 #pragma unroll UNR
             for (int i = 0; i < n; ++i) {
@@ -45,16 +46,18 @@ struct StepJvpBody {
                 const double z = m.fat(j, 0) * hv;
                 const double g = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
 #pragma unroll UNR3
-                for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + 3 * n + j) * U + u] = (r == 2 * n + j) ? g : 0.0;
+                for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + 3 * n + j) * UJ + u] = (r == 2 * n + j) ? g : 0.0;
             }
         }
     }
 };
 
 cudaError_t launch_step_jvp(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
-                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s)
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, cudaStream_t s, long cnt, long UJ)
 {
-    return dispatch<StepJvpBody>(m, U, 3 * m.n + 1, s, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac);
+    if (cnt < 0) cnt = U;
+    if (UJ <= 0) UJ = U;
+    return dispatch<StepJvpBody>(m, cnt, 3 * m.n + 1, s, U, UJ, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac);
 }
 
 }  // namespace mpcf

@@ -48,10 +48,12 @@ size_t jvp_ws_doubles_per_unit(int n) { return (size_t)4 * (3 * n * n + 4 * n); 
 // ------------------------------------------------------------------------------------------------ K1
 template <int N, int L>
 __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt,
-                                                         const double *q, const double *qd, const double *tau, const double *f,
-                                                         double dt, const double *dt_u, double *qn, double *qdn, double *fn,
-                                                         double *ws)
+                                                         const double *q, const double *qd, const double *tau, const double *theat,
+                                                         long UT, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
+                                                         double *fn, double *ws)
 {
+    // theat: the torque that heats the windings (fatigue right-hand side); equals tau unless the model couples the arms'
+    // fatigue through a shared load (kernels_couple.cu), in which case the dynamics still see tau
     static_assert(N == L, "the pipeline runs one serial chain at a time (forests: one launch per chain)");
     const StaticModel<N, L> m{P};
     using D = Dyn<double, StaticModel<N, L>>;
@@ -59,13 +61,14 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
     const long lu = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (lu >= cnt) return;
     const long u = u0 + lu;
-    double x[3 * N], t[N], xs[3 * N], xn[3 * N], k[3 * N];
+    double x[3 * N], t[N], th[N], xs[3 * N], xn[3 * N], k[3 * N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         x[i] = q[i * U + u];
         x[N + i] = qd[i * U + u];
         x[2 * N + i] = f[i * U + u];
         t[i] = tau[i * U + u];
+        th[i] = theat[i * UT + u];
     }
     const double h = dt_u ? dt_u[u] : dt;
 #pragma unroll
@@ -81,7 +84,7 @@ __global__ void __launch_bounds__(kThreads) k_step_stages(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 k[i] = xs[N + i];
-                k[2 * N + i] = D::fatigue_rhs(m, i, xs[2 * N + i], t[i], xs[N + i]);
+                k[2 * N + i] = D::fatigue_rhs(m, i, xs[2 * N + i], th[i], xs[N + i]);
             }
             double *c = ws + W::chunk(lu / 32, s) + 2 * N * N * 32 + (lu & 31);
 #pragma unroll
@@ -558,7 +561,7 @@ struct ColumnState {
     // there only the own rows are written (every chain's launch writes its part).
     // WHOLE: the chain is the whole model (ntot = N, c0 = 0) and every offset is a compile-time constant
     template <bool WHOLE>
-    MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac, int ntot_, int c0_) const
+    MPCF_DI void store(const StaticParams<N> &P, int col, double h, long U, long u, double *jac, int ntot_, int c0_) const  // U = plane stride of jac
     {
         const int ntot = WHOLE ? N : ntot_, c0 = WHOLE ? 0 : c0_;
         const long PC = 4 * ntot + 1;
@@ -640,8 +643,8 @@ MPCF_DI void tma_issue(unsigned item, double *buf, unsigned long long *full, uns
 // starts its own stage (the slot is free by then unless the whole CTA is memory-starved).
 template <int N, int L, int NBUF, int CPW, bool WHOLE>
 __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
-    k_chain_rule_tma(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
-                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, int ntot, int c0)
+    k_chain_rule_tma(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, long UT, double dt,
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, long UJ, int ntot, int c0)
 {
     using W = WsLayout<N>;
     constexpr int NC = 3 * N + 1;
@@ -672,10 +675,10 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
         const double h = dt_u ? dt_u[u] : dt;
         ColumnState<N, L> a, b;
         a.init(col0);
-        a.set_tau(P, a.jt >= 0 ? tau[(size_t)a.jt * U + u] : 0.0);
+        a.set_tau(P, a.jt >= 0 ? tau[(size_t)a.jt * UT + u] : 0.0);  // tau here = the heating torque (plane stride UT)
         if (CPW == 2) {
             b.init(two ? col1 : col0);
-            b.set_tau(P, b.jt >= 0 ? tau[(size_t)b.jt * U + u] : 0.0);
+            b.set_tau(P, b.jt >= 0 ? tau[(size_t)b.jt * UT + u] : 0.0);
         }
 #pragma unroll 1
         for (int s = 0; s < 4; ++s, ++it) {
@@ -689,8 +692,8 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
             if (lane == 0) mbar_arrive(&empty[slot]);
         }
         if (live) {
-            a.template store<WHOLE>(P, col0, h, U, u, jac, ntot, c0);
-            if (two) b.template store<WHOLE>(P, col1, h, U, u, jac, ntot, c0);
+            a.template store<WHOLE>(P, col0, h, UJ, u, jac, ntot, c0);
+            if (two) b.template store<WHOLE>(P, col1, h, UJ, u, jac, ntot, c0);
         }
     }
 }
@@ -699,8 +702,8 @@ __global__ void __launch_bounds__(32 * ((3 * N + CPW) / CPW), 1)
 // straight from the workspace tile with immediate plane offsets.
 template <int N, int L, int NCY>
 __global__ void __launch_bounds__(32 * NCY, 2)
-    k_chain_rule_ldg(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, double dt,
-                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, int ntot, int c0)
+    k_chain_rule_ldg(const __grid_constant__ StaticParams<N> P, long U, long u0, long cnt, const double *__restrict__ tau, long UT, double dt,
+                     const double *__restrict__ dt_u, const double *__restrict__ ws, double *__restrict__ jac, long UJ, int ntot, int c0)
 {
     using W = WsLayout<N>;
     const long lu = (long)blockIdx.x * 32 + threadIdx.x;
@@ -711,10 +714,10 @@ __global__ void __launch_bounds__(32 * NCY, 2)
     for (int col = threadIdx.y; col < NC; col += blockDim.y) {
         ColumnState<N, L> st;
         st.init(col);
-        st.set_tau(P, st.jt >= 0 ? tau[(size_t)st.jt * U + u] : 0.0);
+        st.set_tau(P, st.jt >= 0 ? tau[(size_t)st.jt * UT + u] : 0.0);
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) st.stage(P, s, ws + W::chunk(blockIdx.x, s) + threadIdx.x, h);
-        st.template store<false>(P, col, h, U, u, jac, ntot, c0);
+        st.template store<false>(P, col, h, UJ, u, jac, ntot, c0);
     }
 }
 
@@ -780,8 +783,9 @@ static int sm_count()
 }
 
 template <int N, int L>
-static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, const double *qd, const double *tau, const double *f,
-                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws, long Uc,
+static cudaError_t run_jvp2(const StaticParams<N> &P, long U, long Ucnt, const double *q, const double *qd, const double *tau, const double *theat,
+                            long UT, const double *f,
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, long UJ, double *ws, long Uc,
                             cudaStream_t s, int ntot = N, int c0 = 0)
 {
     using W = WsLayout<N>;
@@ -821,12 +825,12 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
             attr_set[dev].store(true, std::memory_order_release);
         }
     }
-    for (long u0 = 0; u0 < U; u0 += Uc) {
-        const long cnt = (U - u0) < Uc ? (U - u0) : Uc;
+    for (long u0 = 0; u0 < Ucnt; u0 += Uc) {
+        const long cnt = (Ucnt - u0) < Uc ? (Ucnt - u0) : Uc;
         const unsigned gb = (unsigned)((cnt + kThreads - 1) / kThreads);
         const long ntiles = (cnt + 31) / 32;
         cudaEvent_t pe = prof_begin(0, s);
-        k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, ws);
+        k_step_stages<N, L><<<gb, kThreads, 0, s>>>(P, U, u0, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, ws);
         prof_end(pe, s);
         pe = prof_begin(1, s);
         static const int k2smem = getenv("MPCF_K2_SMEM") ? atoi(getenv("MPCF_K2_SMEM")) : 1;
@@ -846,13 +850,13 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
             const int cpw = kCpwDefault == 2 ? 2 : cpw_env;
             if (cpw == 2) {
                 (ntot == N ? k_chain_rule_tma<N, L, NBUF, 2, true> : k_chain_rule_tma<N, L, NBUF, 2, false>)<<<g3, 32 * ((3 * N + 2) / 2), smem, s>>>(
-                    P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+                    P, U, u0, cnt, theat, UT, dt, dt_u, ws, jac, UJ, ntot, c0);
             } else if constexpr (kCpwDefault == 1) {
                 (ntot == N ? k_chain_rule_tma<N, L, NBUF, 1, true> : k_chain_rule_tma<N, L, NBUF, 1, false>)<<<g3, 32 * (3 * N + 1), smem, s>>>(
-                    P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+                    P, U, u0, cnt, theat, UT, dt, dt_u, ws, jac, UJ, ntot, c0);
             }
         } else {
-            k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, tau, dt, dt_u, ws, jac, ntot, c0);
+            k_chain_rule_ldg<N, L, 10><<<(unsigned)ntiles, dim3(32, 10), 0, s>>>(P, U, u0, cnt, theat, UT, dt, dt_u, ws, jac, UJ, ntot, c0);
         }
         prof_end(pe, s);
         g_launches.fetch_add(3);
@@ -863,14 +867,15 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, const double *q, c
 // Forests: the chains are dynamically decoupled, so each runs the single-chain pipeline on its own input planes and writes its
 // block of the whole-model Jacobian (plus the zeros of the cross blocks).
 template <int L>
-static cudaError_t run_forest(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f, double dt,
-                              const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws, long Uc, cudaStream_t s)
+static cudaError_t run_forest(const LaunchModel &m, long U, long Ucnt, const double *q, const double *qd, const double *tau, const double *theat,
+                              long UT, const double *f, double dt,
+                              const double *dt_u, double *qn, double *qdn, double *fn, double *jac, long UJ, double *ws, long Uc, cudaStream_t s)
 {
     const StaticParams<L> *cp = static_cast<const StaticParams<L> *>(m.chain_params);
     for (int c = 0; c < m.n / L; ++c) {
         const size_t off = (size_t)c * L * U;
-        cudaError_t e = run_jvp2<L, L>(cp[c], U, q + off, qd + off, tau + off, f + off, dt, dt_u, qn ? qn + off : nullptr,
-                                       qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, ws, Uc, s, m.n, L * c);
+        cudaError_t e = run_jvp2<L, L>(cp[c], U, Ucnt, q + off, qd + off, tau + off, theat + (size_t)c * L * UT, UT, f + off, dt, dt_u, qn ? qn + off : nullptr,
+                                       qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, UJ, ws, Uc, s, m.n, L * c);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -880,24 +885,29 @@ bool jvp2_supported(const LaunchModel &m) { return family_chain_len(m.fam) > 0; 
 
 cudaError_t launch_step_jvp_ws(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
                                double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, double *ws,
-                               size_t ws_bytes, cudaStream_t s)
+                               size_t ws_bytes, cudaStream_t s, long cnt, long UJ, const double *theat, long UT)
 {
-    if (U <= 0) return cudaSuccess;
+    if (!theat) { theat = tau; UT = U; }  // uncoupled model: the commanded torque is what heats the windings
+    // cnt units are evaluated; U is the plane stride of the input / state arrays, UJ that of the Jacobian planes (callers
+    // evaluating a unit range of a larger batch pass base pointers shifted to the range and a chunk-local Jacobian buffer)
+    if (cnt < 0) cnt = U;
+    if (UJ <= 0) UJ = U;
+    if (cnt <= 0) return cudaSuccess;
     const size_t per_unit = jvp_ws_doubles_per_unit(family_chain_len(m.fam)) * sizeof(double);
     long Uc = (long)(ws_bytes / per_unit);
     Uc -= Uc % 32;  // whole 32-unit tiles
     if (Uc < 32) return cudaErrorInvalidValue;
     switch (m.fam) {
     case FAM_CHAIN3:
-        return run_jvp2<3, 3>(*static_cast<const StaticParams<3> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+        return run_jvp2<3, 3>(*static_cast<const StaticParams<3> *>(m.static_params), U, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, Uc, s);
     case FAM_CHAIN6:
-        return run_jvp2<6, 6>(*static_cast<const StaticParams<6> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+        return run_jvp2<6, 6>(*static_cast<const StaticParams<6> *>(m.static_params), U, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, Uc, s);
     case FAM_CHAIN7:
-        return run_jvp2<7, 7>(*static_cast<const StaticParams<7> *>(m.static_params), U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+        return run_jvp2<7, 7>(*static_cast<const StaticParams<7> *>(m.static_params), U, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, Uc, s);
     case FAM_FOREST12x6:
-        return run_forest<6>(m, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+        return run_forest<6>(m, U, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, Uc, s);
     case FAM_FOREST14x7:
-        return run_forest<7>(m, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, Uc, s);
+        return run_forest<7>(m, U, cnt, q, qd, tau, theat, UT, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, Uc, s);
     default:
         return cudaErrorInvalidValue;
     }

@@ -26,8 +26,8 @@ struct AbaBody {
 struct StepBody {
     static constexpr int kGenericMinBlocks = 3;
     template <class MP>
-    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, const double *f,
-                            double dt, const double *dt_u, double *qn, double *qdn, double *fn)
+    static MPCF_DI void run(const MP &m, long u, long U, const double *q, const double *qd, const double *tau, const double *theat,
+                            const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn)
     {
         constexpr int UNR = MP::kStatic ? MP::MAXN : 1;
         const int n = m.n();
@@ -40,7 +40,11 @@ struct StepBody {
             t[i] = tau[i * U + u];
         }
         const double h = dt_u ? dt_u[u] : dt;
-        Dyn<double, MP>::step_rk4(m, x, t, h, xn);
+        // coupled fatigue: the windings heat with theat while the dynamics see tau (one call site: the step body is ~50 KB of code)
+        double th[MP::MAXN];
+#pragma unroll UNR
+        for (int i = 0; i < n; ++i) th[i] = theat ? theat[i * U + u] : t[i];
+        Dyn<double, MP>::step_rk4(m, x, t, th, h, xn);
 #pragma unroll UNR
         for (int i = 0; i < n; ++i) {
             qn[i * U + u] = xn[i];
@@ -98,9 +102,9 @@ cudaError_t launch_aba(const LaunchModel &m, long U, const double *q, const doub
     return dispatch<AbaBody>(m, U, 1, s, q, qd, tau, qdd);
 }
 cudaError_t launch_step(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, const double *f,
-                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s)
+                        double dt, const double *dt_u, double *qn, double *qdn, double *fn, cudaStream_t s, const double *theat)
 {
-    return dispatch<StepBody>(m, U, 1, s, q, qd, tau, f, dt, dt_u, qn, qdn, fn);
+    return dispatch<StepBody>(m, U, 1, s, q, qd, tau, theat, f, dt, dt_u, qn, qdn, fn);
 }
 
 }  // namespace mpcf

@@ -224,6 +224,27 @@ class BatchEvaluator:
                 C.c_void_p(fn.data_ptr()), C.c_void_p(jac.data_ptr()), ws, ws_bytes, _stream()))
         return qn, qdn, fn, jac
 
+    def step_rk4_jvp_range(self, q, qd, tau, f, dt: float, u0: int, cnt: int, out, jac):
+        """Units [u0, u0 + cnt) of a larger batch: states go to columns [u0, u0 + cnt) of the full-size `out` = (qn, qdn, fn),
+        the Jacobian to the chunk-local buffer jac[3n, 4n+1, cap] (cap >= cnt) — one Jacobian buffer is reused over the
+        chunks of a batch whose dense Jacobian would not fit the device (configs C3, C4, C5)."""
+        U, n = self._U(q), self.n
+        if not (0 <= u0 and cnt >= 0 and u0 + cnt <= U):
+            raise ValueError("unit range out of bounds")
+        qn, qdn, fn = out
+        for t, nm in ((q, "q"), (qd, "qd"), (tau, "tau"), (f, "f"), (qn, "qn"), (qdn, "qdn"), (fn, "fn")):
+            self._in(t, n, U, nm)
+        if not (jac.is_cuda and jac.dtype == torch.float64 and jac.is_contiguous() and jac.dim() == 3
+                and tuple(jac.shape[:2]) == (3 * n, 4 * n + 1) and jac.shape[2] >= cnt and jac.device == self.device):
+            raise ValueError("jac must be a contiguous CUDA float64 tensor [3n, 4n+1, cap >= cnt]")
+        off = lambda t: C.c_void_p(t.data_ptr() + 8 * u0)
+        with torch.cuda.device(self.device):
+            ws, ws_bytes = self._workspace(cnt)
+            _capi.check(_capi.lib.mpcf_step_rk4_jvp_strided_batch(
+                self.model.handle, cnt, U, off(q), off(qd), off(tau), off(f), float(dt), None, off(qn), off(qdn), off(fn),
+                C.c_void_p(jac.data_ptr()), jac.shape[2], ws, ws_bytes, _stream()))
+        return jac
+
     def cost_residual(self, B: int, N: int, q, qd, f, tau, qn, qdn, fn, dt: float, w_qd=1.0, w_tau=1e-2, tau0=50.0,
                       alpha=2.0, tau_floor=15.0, f_max=80.0, out=None):
         """Per-scenario (cost, defect, torque-bound, fatigue-bound) -> out[4, B]; units are node-major u = k*B + b."""
@@ -235,3 +256,24 @@ class BatchEvaluator:
                                                            float(tau0), float(alpha), float(tau_floor), float(f_max),
                                                            C.c_void_p(o.data_ptr()), _stream()))
         return o
+
+    def cost_residual_table(self, B: int, N: int, q, qd, f, tau, qn, qdn, fn, bound_table, w_qd=1.0, w_tau=1e-2, f_max=80.0, out=None,
+                            out_col0: int = 0):
+        """Same reduction with a per-node, per-joint torque-bound table `bound_table` [N, n, 2] = (lb, ub) (device tensor; build it
+        with ocp.f0_bound_table / ocp.step_bound_table / ocp.switch_off_bound_table).  With `out` = a [4, B_total] buffer and
+        `out_col0`, the B scenarios of this call fill columns [out_col0, out_col0 + B) (scenario chunks of one send buffer)."""
+        n, U = self.n, B * N
+        if out is None:
+            out = torch.empty((4, B), dtype=torch.float64, device=self.device)
+        if not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.dim() == 2 and out.shape[0] == 4
+                and 0 <= out_col0 and out_col0 + B <= out.shape[1] and out.device == self.device):
+            raise ValueError("out must be a contiguous CUDA float64 tensor [4, >= out_col0 + B]")
+        tb = bound_table
+        if not (tb.is_cuda and tb.dtype == torch.float64 and tb.is_contiguous() and tuple(tb.shape) == (N, n, 2) and tb.device == self.device):
+            raise ValueError("bound_table must be a contiguous CUDA float64 tensor of shape (N, n, 2)")
+        args = [self._in(t, n, U, nm) for t, nm in ((q, "q"), (qd, "qd"), (f, "f"), (tau, "tau"), (qn, "qn"), (qdn, "qdn"), (fn, "fn"))]
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_cost_residual_table_batch(self.model.handle, B, N, *args, float(w_qd), float(w_tau),
+                                                                 C.c_void_p(tb.data_ptr()), float(f_max),
+                                                                 C.c_void_p(out.data_ptr() + 8 * out_col0), out.shape[1], _stream()))
+        return out if out.shape[1] != B else out

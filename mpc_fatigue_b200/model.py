@@ -108,3 +108,16 @@ class Model:
     def set_fatigue(self, rows) -> None:
         a = np.ascontiguousarray(np.broadcast_to(np.asarray(rows, dtype=np.float64), (self.n, 4)))
         _capi.check(_capi.lib.mpcf_model_set_fatigue(self._h, a.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_coupling(self, coupling) -> None:
+        """Couple the two arms' fatigue through a shared box load: `coupling` = (ee_frame_arm0, ee_frame_arm1, weight) with frame
+        indices (or names) and the box weight m g; None removes it (include/mpcf.h: mpcf_model_set_coupling)."""
+        if coupling is None:
+            _capi.check(_capi.lib.mpcf_model_set_coupling(self._h, None))
+            self.coupling = None
+            return
+        f0, f1, w = coupling
+        fr = [self.frame_id(f) if isinstance(f, str) else int(f) for f in (f0, f1)]
+        c = _capi.Coupling((C.c_int * 2)(*fr), float(w))
+        _capi.check(_capi.lib.mpcf_model_set_coupling(self._h, C.byref(c)))
+        self.coupling = (fr[0], fr[1], float(w))

@@ -80,6 +80,32 @@ def step_bound_table(N: int, segments: list[tuple[np.ndarray, np.ndarray]]) -> t
     return lb, ub
 
 
+def f0_bound_table(N: int, n: int, h: float, tau0: float = 50.0, alpha: float = 2.0, floor: float = 15.0) -> np.ndarray:
+    """F0 as a [N, n, 2] (lb, ub) table for mpcf_cost_residual_table_batch: -b_k <= tau <= b_k on every joint."""
+    b = f0_bound_schedule(N, h, tau0, alpha, floor)
+    return np.ascontiguousarray(np.stack([-b[:, None].repeat(n, 1), b[:, None].repeat(n, 1)], axis=-1))
+
+
+def bound_table_from(lb: np.ndarray, ub: np.ndarray) -> np.ndarray:
+    """[N, n] lower / upper arrays (e.g. from step_bound_table) -> [N, n, 2] table."""
+    return np.ascontiguousarray(np.stack([np.asarray(lb, dtype=np.float64), np.asarray(ub, dtype=np.float64)], axis=-1))
+
+
+def switch_off_bound_table(N: int, lbtorque, ubtorque, S, C) -> np.ndarray:
+    """F3 joint switch-off (python/Centauro_script/Centauro_dynamics.py:327-348, strings S / C of CentaurOCP.py:64-71): joints
+    with S[i] = 1 keep their torque limits for k < int(N / 3) and are clamped to |tau_i| <= C[i] afterwards; the others keep
+    [lbtorque_i, ubtorque_i] over the whole horizon.  Returns the [N, n, 2] (lb, ub) table."""
+    lbt, ubt = np.asarray(lbtorque, dtype=np.float64), np.asarray(ubtorque, dtype=np.float64)
+    S, C = np.asarray(S).astype(bool), np.asarray(C, dtype=np.float64)
+    n = len(lbt)
+    tb = np.empty((N, n, 2))
+    for k in range(N):
+        late = S & (k >= int(N / 3))
+        tb[k, :, 0] = np.where(late, -C, lbt)
+        tb[k, :, 1] = np.where(late, C, ubt)
+    return tb
+
+
 class PilzForceOCP:
     """Node rows of python/Pilz_6_DOF/force_optimization_pilz_6DOF.py for B scenarios at once.
 

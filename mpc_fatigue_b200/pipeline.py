@@ -5,7 +5,8 @@ This is the end-to-end path a CPU-side NLP solver would use in place of the refe
 is cut into chunks; for each chunk the input planes are copied host->device, the RK4+Jacobian kernel and the
 per-scenario cost/residual reduction run, and states + dense Jacobian + reduced rows are copied
 device->host into pinned staging.  Three streams (H2D, compute, D2H) and two buffer slots overlap the
-copies of neighbouring chunks with compute.  Host layout = device layout: `[component, N, B]` planes with
+copies of neighbouring chunks with compute.  What goes back is first packed on the device (mpcf_gather_planes: states + the
+selected Jacobian planes -> one contiguous buffer), so every chunk returns in ONE device->host copy.  Host layout = device layout: `[component, N, B]` planes with
 node-major units, so a scenario chunk of every plane is one pitched DMA (mpcf_memcpy2d_async).
 """
 from __future__ import annotations
@@ -49,14 +50,8 @@ class HostStepPipeline:
                         continue
                     planes.append(3 * n + r * P + c)
         self.plane_map = planes
-        self.segments = []  # (device plane start, host row start, count) of contiguous runs
-        k = 0
-        while k < len(planes):
-            j = k
-            while j + 1 < len(planes) and planes[j + 1] == planes[j] + 1:
-                j += 1
-            self.segments.append((planes[k], k, j - k + 1))
-            k = j + 1
+        self.d_map = torch.tensor(planes, dtype=torch.int32, device=self.dev)
+        self.identity_map = planes == list(range(len(planes)))  # nothing skipped: the output buffer already is the packed form
 
     def _alloc(self, B: int, N: int):
         n = self.n
@@ -69,6 +64,7 @@ class HostStepPipeline:
         self.d_in = [torch.empty((4 * n, Uc), **f64) for _ in range(2)]
         self.d_out = [torch.empty((out_rows, Uc), **f64) for _ in range(2)]
         self.d_red = [torch.empty((4, Bc), **f64) for _ in range(2)]
+        self.d_pack = None if (self.identity_map or self.outputs != "all") else [torch.empty((len(self.plane_map), Uc), **f64) for _ in range(2)]
         self.h_out = [torch.empty((len(self.plane_map), Uc), dtype=torch.float64).pin_memory() for _ in range(2)]
         self.h_red = torch.empty((4, B), dtype=torch.float64).pin_memory()
         self.reduced = torch.empty((4, B), **f64)
@@ -144,9 +140,14 @@ class HostStepPipeline:
                     if consume is not None and len(pending) == 2:  # the slot about to be overwritten goes to the consumer first
                         hand_over(pending.pop(0))
                     with torch.cuda.stream(self.s_out):
-                        hflat, dflat = self.h_out[slot].reshape(-1), d_out.reshape(-1)
-                        for dp, hr, cnt in self.segments:  # one DMA per contiguous run of planes
-                            hflat[hr * uc:(hr + cnt) * uc].copy_(dflat[dp * uc:(dp + cnt) * uc], non_blocking=True)
+                        hflat = self.h_out[slot].reshape(-1)
+                        if self.d_pack is None:
+                            packed = d_out.reshape(-1)
+                        else:  # pack the planes that travel into one contiguous buffer (device copy kernel), then ONE D2H
+                            packed = self.d_pack[slot].reshape(-1)
+                            _capi.check(_capi.lib.mpcf_gather_planes(C.c_void_p(d_out.data_ptr()), uc, C.c_void_p(self.d_map.data_ptr()), hrows, uc,
+                                                                     C.c_void_p(packed.data_ptr()), C.c_void_p(self.s_out.cuda_stream)))
+                        hflat[:hrows * uc].copy_(packed[:hrows * uc], non_blocking=True)
                     d2h += hrows * uc * 8
                 ev_out[slot] = torch.cuda.Event()
                 ev_out[slot].record(self.s_out)

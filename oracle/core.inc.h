@@ -432,6 +432,55 @@ static int SUF(step_rk4)(const mpcfo_model *m, const SC *x, const SC *tau, SC dt
     return rc;
 }
 
+/* ---- coupled fatigue of a two-arm model carrying one box (config C3; builder-defined, PARITY UNPINNED: the reference has no
+ * dynamics-mode fatigue at all — what it has is the box equilibrium F_L,z + F_R,z = m g of python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:197,272-274
+ * and tau = ID - J^T F of :292-293).  Definition, zero-order hold over the step like tau itself:
+ *   Phi_c   = sum of the fatigue states of arm c at the start of the step
+ *   s_c     = Phi_other / (Phi_0 + Phi_1)            share of the box weight arm c carries: the less fatigued arm takes more
+ *   g_c(q)  = J_ee,c(q)^T [0, 0, w, 0, 0, 0]         torque that holds the whole box weight w = m g at arm c's end-effector
+ *   theat_i = tau_i + s_c(i) g_i(q(t_k))             torque the motor of joint i delivers (motion + payload feed-forward)
+ * and the step is x+ = RK4 of (qd, ABA(q, qd, tau), fatigue_rhs(f, theat, qd)): the dynamics see tau, the windings heat with theat.
+ * The two arms are coupled through s_c (d f+_L / d f_R != 0) and the fatigue rows depend on q through g. */
+static int SUF(xdot_heat)(const mpcfo_model *m, const SC *x, const SC *tau, const SC *theat, SC *k)
+{
+    int n = m->n;
+    int rc = SUF(aba)(m, x, x + n, tau, k + n);
+    for (int i = 0; i < n; ++i) {
+        k[i] = x[n + i];
+        k[2 * n + i] = SUF(fatigue_rhs)(m, i, x[2 * n + i], theat[i], x[n + i]);
+    }
+    return rc;
+}
+static void SUF(coupled_heat_torque)(const mpcfo_model *m, const mpcfo_coupling *cp, const SC *q, const SC *f, const SC *tau, SC *theat)
+{
+    int n = m->n;
+    SC Phi[2] = {0, 0}, J[6 * MAXN];
+    for (int i = 0; i < n; ++i) Phi[cp->chain_of[i]] += f[i];
+    SC S = Phi[0] + Phi[1];
+    SC share[2] = {Phi[1] / S, Phi[0] / S};
+    for (int i = 0; i < n; ++i) theat[i] = tau[i];
+    for (int c = 0; c < 2; ++c) {
+        SUF(frame_jacobian)(m, cp->ee_frame[c], q, J);
+        for (int i = 0; i < n; ++i)
+            if (cp->chain_of[i] == c) theat[i] += share[c] * (J[2 * n + i] * cp->weight);
+    }
+}
+static int SUF(step_rk4_coupled)(const mpcfo_model *m, const mpcfo_coupling *cp, const SC *x, const SC *tau, SC dt, SC *xn)
+{
+    int n = m->n, n3 = 3 * m->n, rc = 0;
+    SC k1[3 * MAXN], k2[3 * MAXN], k3[3 * MAXN], k4[3 * MAXN], xs[3 * MAXN], theat[MAXN];
+    SUF(coupled_heat_torque)(m, cp, x, x + 2 * n, tau, theat);
+    rc |= SUF(xdot_heat)(m, x, tau, theat, k1);
+    for (int i = 0; i < n3; ++i) xs[i] = x[i] + 0.5 * dt * k1[i];
+    rc |= SUF(xdot_heat)(m, xs, tau, theat, k2);
+    for (int i = 0; i < n3; ++i) xs[i] = x[i] + 0.5 * dt * k2[i];
+    rc |= SUF(xdot_heat)(m, xs, tau, theat, k3);
+    for (int i = 0; i < n3; ++i) xs[i] = x[i] + dt * k3[i];
+    rc |= SUF(xdot_heat)(m, xs, tau, theat, k4);
+    for (int i = 0; i < n3; ++i) xn[i] = x[i] + dt / 6.0 * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+    return rc;
+}
+
 /* ---- reference-mode node evaluation (pinned by the plotter fixtures):
  *   tau   = RNEA(q, qd, qdd) + wsign * sum_e J_e^T W_e         (Box_Pilz_6DOF2.py:292-293: wsign=-1;
  *                                                               mpc_principal.py:269: wsign=+1)

@@ -203,6 +203,57 @@ int mpcfo_step_rk4_jvp_batch(const mpcfo_model *m, long U, const double *q, cons
     return rc ? -3 : 0;
 }
 
+int mpcfo_step_rk4_coupled_batch(const mpcfo_model *m, const mpcfo_coupling *cp, long U, const double *q, const double *qd,
+                                 const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
+                                 double *fn)
+{
+    CHECK_N(m);
+    int n = m->n, rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double x[3 * MPCFO_MAXN], t[MPCFO_MAXN], xn[3 * MPCFO_MAXN];
+        for (int i = 0; i < n; ++i) {
+            x[i] = q[i * U + u]; x[n + i] = qd[i * U + u]; x[2 * n + i] = f[i * U + u]; t[i] = tau[i * U + u];
+        }
+        rc |= step_rk4_coupled_r(m, cp, x, t, dt_u ? dt_u[u] : dt, xn) != 0;
+        for (int i = 0; i < n; ++i) {
+            qn[i * U + u] = xn[i]; qdn[i * U + u] = xn[n + i]; fn[i * U + u] = xn[2 * n + i];
+        }
+    }
+    return rc ? -3 : 0;
+}
+
+int mpcfo_step_rk4_coupled_jvp_batch(const mpcfo_model *m, const mpcfo_coupling *cp, long U, const double *q, const double *qd,
+                                     const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
+                                     double *fn, double *jac)
+{
+    CHECK_N(m);
+    const int n = m->n, P = 4 * n + 1;
+    const double hstep = 1e-40;
+    int rc = 0;
+#pragma omp parallel for schedule(static) reduction(| : rc)
+    for (long u = 0; u < U; ++u) {
+        double complex x[3 * MPCFO_MAXN], t[MPCFO_MAXN], xn[3 * MPCFO_MAXN], h;
+        for (int d = 0; d < P; ++d) {
+            for (int i = 0; i < n; ++i) {
+                x[i] = q[i * U + u]; x[n + i] = qd[i * U + u]; x[2 * n + i] = f[i * U + u]; t[i] = tau[i * U + u];
+            }
+            h = dt_u ? dt_u[u] : dt;
+            if (d < 2 * n) x[d] += hstep * I;
+            else if (d < 3 * n) t[d - 2 * n] += hstep * I;
+            else if (d < 4 * n) x[d - n] += hstep * I;
+            else h += hstep * I;
+            rc |= step_rk4_coupled_c(m, cp, x, t, h, xn) != 0;
+            for (int r = 0; r < 3 * n; ++r) jac[((long)r * P + d) * U + u] = cimag(xn[r]) / hstep;
+            if (d == 0 && qn)
+                for (int i = 0; i < n; ++i) {
+                    qn[i * U + u] = creal(xn[i]); qdn[i * U + u] = creal(xn[n + i]); fn[i * U + u] = creal(xn[2 * n + i]);
+                }
+        }
+    }
+    return rc ? -3 : 0;
+}
+
 int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,
                             double h, double *Tnext)
 {

@@ -38,6 +38,13 @@ typedef struct {
     const double *fp;    /* [nframes][3] */
 } mpcfo_model;
 
+/* coupled fatigue of a two-arm model carrying one box (core.inc.h: step_rk4_coupled) */
+typedef struct {
+    const int *chain_of; /* [n] arm index (0 / 1) of every joint */
+    int ee_frame[2];     /* end-effector frame of each arm */
+    double weight;       /* box weight m g */
+} mpcfo_coupling;
+
 int mpcfo_set_threads(int nthreads); /* returns the thread count in use (OpenMP) */
 
 int mpcfo_rnea_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
@@ -56,6 +63,14 @@ int mpcfo_step_rk4_batch(const mpcfo_model *m, long U, const double *q, const do
 int mpcfo_step_rk4_jvp_batch(const mpcfo_model *m, long U, const double *q, const double *qd,
                              const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                              double *qdn, double *fn, double *jac);
+
+/* the same two entries for the coupled-fatigue step (cp: see mpcfo_coupling) */
+int mpcfo_step_rk4_coupled_batch(const mpcfo_model *m, const mpcfo_coupling *cp, long U, const double *q, const double *qd,
+                                 const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
+                                 double *fn);
+int mpcfo_step_rk4_coupled_jvp_batch(const mpcfo_model *m, const mpcfo_coupling *cp, long U, const double *q, const double *qd,
+                                     const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
+                                     double *fn, double *jac);
 
 /* exact zero-order-hold fatigue/thermal map and the ODE right-hand side, element-wise per joint */
 int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,

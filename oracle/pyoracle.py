@@ -145,6 +145,64 @@ class Oracle:
             raise ZeroDivisionError("ABA singular")
         return qn, qdn, fn, jac
 
+    def _coupling(self, ee_frames, weight):
+        n = self.n
+        par = self._a["parent"]
+        root = list(range(n))
+        for i in range(n):
+            root[i] = i if par[i] < 0 else root[par[i]]
+        roots = sorted(set(root))
+        assert len(roots) == 2, "coupled fatigue needs a two-arm model"
+        chain_of = np.ascontiguousarray(np.array([roots.index(r) for r in root], dtype=np.int32))
+
+        class _Cpl(C.Structure):
+            _fields_ = [("chain_of", _IP), ("ee_frame", C.c_int * 2), ("weight", C.c_double)]
+        cp = _Cpl()
+        cp.chain_of = chain_of.ctypes.data_as(_IP)
+        cp.ee_frame = (C.c_int * 2)(*[int(x) for x in ee_frames])
+        cp.weight = float(weight)
+        cp._keep = chain_of
+        return cp
+
+    def step_rk4_coupled(self, ee_frames, weight, q, qd, tau, f, dt, dt_u=None, jac=False):
+        """Coupled-fatigue RK4 step of a two-arm model (core.inc.h: step_rk4_coupled); jac=True adds the complex-step Jacobian."""
+        n, U = q.shape
+        cp = self._coupling(ee_frames, weight)
+        qn, qdn, fn = np.empty((n, U)), np.empty((n, U)), np.empty((n, U))
+        args = [self._ref(), C.byref(cp), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)), _p(_chk(tau, n, U)), _p(_chk(f, n, U)),
+                C.c_double(dt), _p(dt_u), _p(qn), _p(qdn), _p(fn)]
+        if jac:
+            J = np.empty((3 * n, 4 * n + 1, U))
+            rc = self.lib.mpcfo_step_rk4_coupled_jvp_batch(*args, _p(J))
+        else:
+            rc = self.lib.mpcfo_step_rk4_coupled_batch(*args)
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular")
+        return (qn, qdn, fn, J) if jac else (qn, qdn, fn)
+
+    def step_rk4_jvp_forward(self, q, qd, tau, f, dt, dt_u=None):
+        """Same result as step_rk4_jvp by ONE forward-mode sweep per unit with all 3n + 1 directions in SIMD lanes
+        (oracle/forward_mode.cpp, -O3 -march=native, OpenMP): the CPU baseline of bench.py.  n <= 7."""
+        lib = getattr(self, "_fwd", None)
+        if lib is None:
+            path = os.path.join(_HERE, "_build", "libmpcf_oracle_fwd.so")
+            if not os.path.exists(path):
+                build()
+            lib = self._fwd = C.CDLL(path)
+            lib.mpcfo_fwd_set_threads(int(self.threads))
+        n, U = q.shape
+        P = 4 * n + 1
+        qn, qdn, fn = np.empty((n, U)), np.empty((n, U)), np.empty((n, U))
+        jac = np.empty((3 * n, P, U))
+        rc = lib.mpcfo_step_rk4_jvp_forward_batch(self._ref(), C.c_long(U), _p(_chk(q, n, U)), _p(_chk(qd, n, U)),
+                                                  _p(_chk(tau, n, U)), _p(_chk(f, n, U)), C.c_double(dt), _p(dt_u),
+                                                  _p(qn), _p(qdn), _p(fn), _p(jac))
+        if rc == -1:
+            raise ValueError("forward-mode baseline supports n <= 7")
+        if rc != 0:
+            raise ZeroDivisionError("ABA singular")
+        return qn, qdn, fn, jac
+
     def fatigue_zoh(self, T, tau, qd, h):
         n, U = T.shape
         out = np.empty((n, U))

@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Writes profiles/work_model.json: FP64 operations EXECUTED per unit by the shipped Jacobian kernels, from the ncu counters
+(smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on) of tracked `ncu --set full` raw-page exports, plus the DRAM bytes
+per unit of the same captures.  bench.py reads the file for its roofline object ("instrumented count").
+    python profiles/make_work_model.py
+Re-run after a kernel change together with a fresh capture (profiles/README.md has the ncu command)."""
+import csv
+import json
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+# family -> (raw csv, units per launch, {label: kernel-name regex}, multiplier per label)
+SOURCES = {
+    "chain6": ("r01_jvp_pipeline_v6_raw.csv", 1048576, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule"}, 1),
+    "forest12x6": ("r02/r02_c3_jvp_raw.csv", 409600, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule"}, 1),
+    # run-time tree: one launch = 2560 units x 112 seed directions (blockIdx.y); the counters are per launch
+    "generic64": ("r02/r02_c4_jvp_raw.csv", 2560, {"step_rk4_jvp": "generic_kernel"}, 1),
+}
+
+
+def num(s):
+    try:
+        return float(s.replace(",", ""))
+    except ValueError:
+        return 0.0
+
+
+def main():
+    out = {}
+    for fam, (path, units, labels, mult) in SOURCES.items():
+        full = os.path.join(HERE, path)
+        if not os.path.exists(full):
+            continue
+        rows = list(csv.reader(open(full)))
+        hdr, data = rows[0], rows[2:]
+        ix = {h: i for i, h in enumerate(hdr)}
+        kernels, dram = {}, 0.0
+        for r in data:
+            name = r[ix["Kernel Name"]]
+            label = next((lb for lb, rx in labels.items() if re.search(rx, name)), None)
+            if label is None:
+                continue
+            cyc = num(r[ix["smsp__cycles_elapsed.avg"]])
+            k = kernels.setdefault(label, {"dadd": 0.0, "dmul": 0.0, "dfma": 0.0, "launches": 0, "kernel": name.split("(")[0]})
+            for op in ("dadd", "dmul", "dfma"):
+                k[op] += num(r[ix["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op]]) * cyc / units
+            k["launches"] += 1
+            dram += (num(r[ix["dram__bytes_read.sum"]]) + num(r[ix["dram__bytes_write.sum"]])) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(
+                rows[1][ix["dram__bytes_read.sum"]], 1) / units
+        # a capture that holds the same kernel several times for the SAME units (repeated passes) is averaged; the two chains of
+        # a forest are different work on the same units and are summed
+        reps = 1 if fam != "forest12x6" else 1
+        if fam == "forest12x6":
+            # the capture holds two passes x two chains: launches = 4 per label -> per unit = sum / 2 passes
+            reps = max(1, min(k["launches"] for k in kernels.values()) // 2)
+        for k in kernels.values():
+            for op in ("dadd", "dmul", "dfma"):
+                k[op] = round(k[op] / reps * mult)
+        out[fam] = {"kernels": kernels, "dram_bytes_per_unit": round(dram / reps), "source": "profiles/" + path, "units_per_launch": units}
+    with open(os.path.join(HERE, "work_model.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    for fam, v in out.items():
+        flop = sum(k["dadd"] + k["dmul"] + 2 * k["dfma"] for k in v["kernels"].values())
+        inst = sum(k["dadd"] + k["dmul"] + k["dfma"] for k in v["kernels"].values())
+        print("%-12s %9d FLOP/unit  %9d FP64 instr/unit  %7d DRAM B/unit   (%s)" % (fam, flop, inst, v["dram_bytes_per_unit"], v["source"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import oracle_model_from_export, random_inputs
+from conftest import oracle_model_from_export, random_inputs, rel_err_rows
 from mpc_fatigue_b200.model import Model, data_urdf
 from oracle.pyoracle import Oracle
 from oracle.urdf_model import load_urdf
@@ -146,3 +146,22 @@ def test_gravity_only_static_torque_is_configuration_gradient_of_potential():
         e = np.zeros((6, 1)); e[j] = 1e-6
         g[j] = (potential(q + e) - potential(q - e)) / 2e-6
     assert np.abs(tau - g).max() < 1e-6
+
+
+def test_forward_mode_baseline_matches_the_complex_step_checker():
+    """oracle/forward_mode.cpp (bench.py's CPU baseline: one forward-mode sweep, directions in SIMD lanes, closed-form fatigue
+    columns) against the complex-step instantiation, on the three models it supports (n <= 7)."""
+    from mpc_fatigue_b200.model import data_urdf
+    from oracle.urdf_model import load_urdf
+    for name, U in (("pilz6", 257), ("pilz3", 64)):
+        om = load_urdf(data_urdf(name), armature=1e-2)
+        orc = Oracle(om)
+        q, qd, tau, f, _ = random_inputs(om, U, seed=17)
+        dt_u = np.ascontiguousarray(np.random.default_rng(3).uniform(0.005, 0.03, U))
+        for kw in (dict(dt_u=None), dict(dt_u=dt_u)):
+            ref = orc.step_rk4_jvp(q, qd, tau, f, 0.02, **kw)
+            got = orc.step_rk4_jvp_forward(q, qd, tau, f, 0.02, **kw)
+            for a, b in zip(got[:3], ref[:3]):
+                assert rel_err_rows(a, b) < 1e-13
+            n = om.n
+            assert rel_err_rows(got[3].reshape(3 * n * (4 * n + 1), U), ref[3].reshape(3 * n * (4 * n + 1), U)) < 1e-10
