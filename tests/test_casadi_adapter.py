@@ -106,7 +106,7 @@ def test_dyn_fatigue_step_callback_against_function_and_oracle(adapter):
             B = blocks[o * 5 + i].full()
             for k in range(N):
                 if i < 4:
-                    blk = B[n * k:n * k + n, n * k:n * k + n]
+                    blk = B[n * k:n * k + n, n * k:n * k + n].copy()
                     B[n * k:n * k + n, n * k:n * k + n] = 0.0
                     cols = slice(i * n, (i + 1) * n)
                 else:

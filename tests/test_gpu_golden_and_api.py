@@ -187,7 +187,7 @@ def test_host_pipeline_matches_direct_calls(torch_mod):
     assert torch.equal(pipe.h_red, red.cpu())
     # structural zeros stay on the device: 348 of 450 Jacobian planes travel, mapped by plane_map
     pz = HostStepPipeline(m, "cuda:0", chunk_units=N * 256, skip_structural_zeros=True)
-    assert len(pz.plane_map) == 18 + 348 and len(pz.segments) < 30
+    assert len(pz.plane_map) == 18 + 348 and not pz.identity_map and pipe.identity_map  # packed on the device, one D2H per chunk
     gz = {}
     st2 = pz.run(*host, dt, B, N, consume=lambda v, b0, b1: gz.__setitem__((b0, b1), v.clone()))
     assert st2["d2h_bytes"] == (18 + 348) * B * N * 8 + 4 * B * 8
