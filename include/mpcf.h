@@ -147,7 +147,9 @@ int mpcf_rollout_rk4_batch(const mpcf_model *model, long B, int N, const double 
    Compile-time families ("chain3", "chain6", "chain7", "forest12x6", "forest14x7") run the analytic pipeline (forward-dynamics
    derivatives per RK4 stage + a chain rule through the stages) staged through a device workspace that this entry takes from
    the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on `stream`: no synchronisation, and the pool
-   keeps the block between calls).  Run-time-topology families run 3n + 1 dual-number sweeps. */
+   keeps the block between calls).  Run-time-topology models with n <= 40 (branched trees, prismatic joints: config C4) run the
+   tree form of the same pipeline (ancestor-pattern derivatives, M = L^T D L, one CTA per unit for the chain rule); larger
+   run-time-topology models run 3n + 1 dual-number sweeps. */
 int mpcf_step_rk4_jvp_batch(const mpcf_model *model, long U, const double *q, const double *qd,
                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                             double *qdn, double *fn, double *jac, void *stream);

@@ -29,6 +29,7 @@ struct mpcf_model {
     mutable int device = -1;  // device holding the uploaded blob (run-time-topology families)
     int fd_status = 0;  // 0 unknown, 1 ok, -1 singular
     CoupleHost couple;  // coupled fatigue of a two-arm model (mpcf_model_set_coupling)
+    int npat = 0;       // size of the ancestor pattern sum_k (depth_k + 1): packed storage of the tree Jacobian pipeline
 };
 
 static thread_local std::string g_err;
@@ -98,6 +99,14 @@ static void refresh(mpcf_model *m)
         for (int c = 0; c < 2; ++c) fill_static(h, m->chain7[c], 7 * c);
     }
     else m->fam = h.n <= 16 ? FAM_GENERIC16 : FAM_GENERIC64;
+    {
+        std::vector<int> depth(h.n, 0);
+        m->npat = 0;
+        for (int j = 0; j < h.n; ++j) {
+            depth[j] = h.parent[j] < 0 ? 0 : depth[h.parent[j]] + 1;
+            m->npat += depth[j] + 1;
+        }
+    }
     m->dirty = true;
     m->fd_status = 0;
 }
@@ -307,6 +316,11 @@ static int get_launch_model(const mpcf_model *m, LaunchModel &lm)
         for (int j = 0; j < n; ++j)
             if (h.parent[j] >= 0 && h.parent[j] != j - 1) keep[h.parent[j]] = 1;
         ii.insert(ii.end(), keep.begin(), keep.end());
+        std::vector<int> depth(n, 0), rowptr(n + 1, 0);  // packed ancestor storage of the tree Jacobian pipeline
+        for (int j = 0; j < n; ++j) depth[j] = h.parent[j] < 0 ? 0 : depth[h.parent[j]] + 1;
+        for (int j = 0; j < n; ++j) rowptr[j + 1] = rowptr[j] + depth[j] + 1;
+        ii.insert(ii.end(), depth.begin(), depth.end());
+        ii.insert(ii.end(), rowptr.begin(), rowptr.end());
         cudaError_t e;
         // a setter re-dirtied an uploaded model: kernels queued on any stream may still read the old blob
         if (m->d_dbl && m->device == dev) cudaDeviceSynchronize();
@@ -502,6 +516,8 @@ extern "C" size_t mpcf_step_rk4_jvp_workspace_bytes(const mpcf_model *model, lon
     if (!model || U <= 0) return 0;
     LaunchModel lm;
     lm.fam = model->fam;
+    lm.n = model->h.n;
+    if (tree_jvp_supported(lm)) return tree_jvp_workspace_bytes(model->h.n, model->npat, U);
     if (!jvp2_supported(lm)) return 0;
     long units = U < kJvpChunkUnits ? U : kJvpChunkUnits;
     units = (units + 31) / 32 * 32;
@@ -515,6 +531,8 @@ static cudaError_t run_pipeline(const mpcf_model *model, const LaunchModel &lm, 
                                 const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn,
                                 double *jac, long ld_jac, double *ws, size_t ws_bytes, cudaStream_t st)
 {
+    if (tree_jvp_supported(lm))
+        return launch_step_jvp_tree(lm, model->npat, ld, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ld_jac, ws, ws_bytes, st);
     if (!model->couple.on) return launch_step_jvp_ws(lm, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, ws, ws_bytes, st, cnt, ld_jac);
     double *theat = nullptr;
     cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&theat), (size_t)model->h.n * cnt * sizeof(double), st);
@@ -546,10 +564,12 @@ extern "C" int mpcf_step_rk4_jvp_ws_batch(const mpcf_model *model, long U, const
     PROLOGUE(q && qd && tau && f && jac)
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
-    if (!jvp2_supported(lm))  // run-time topology: no workspace pipeline; the workspace argument is ignored
+    const bool tree = tree_jvp_supported(lm);
+    if (!jvp2_supported(lm) && !tree)  // run-time topology with n > 40: no workspace pipeline; the workspace argument is ignored
         return done(launch_step_jvp(lm, U, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st), "step_rk4_jvp_batch");
     if (U == 0) return MPCF_OK;
-    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
+    const size_t min_ws = tree ? tree_jvp_workspace_bytes(model->h.n, model->npat, 32)
+                               : (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
     if (workspace) {
         // the chain-rule kernel streams the workspace with cp.async.bulk: 16-byte aligned global addresses; chunk offsets
         // are multiples of 256 B, so the base decides.  128 keeps every plane on a full cache line.
@@ -583,9 +603,11 @@ extern "C" int mpcf_step_rk4_jvp_strided_batch(const mpcf_model *model, long cnt
     if ((qn || qdn || fn) && !(qn && qdn && fn)) return fail(MPCF_EINVAL, "qn/qdn/fn must be all set or all NULL");
     if (int rc = check_forward_dynamics(model)) return rc;
     if (cnt == 0) return MPCF_OK;
-    if (!jvp2_supported(lm))
+    const bool tree = tree_jvp_supported(lm);
+    if (!jvp2_supported(lm) && !tree)
         return done(launch_step_jvp(lm, ld, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, st, cnt, ld_jac), "step_rk4_jvp_strided_batch");
-    const size_t min_ws = (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
+    const size_t min_ws = tree ? tree_jvp_workspace_bytes(model->h.n, model->npat, 32)
+                               : (size_t)32 * jvp_ws_doubles_per_unit(family_chain_len(model->fam)) * sizeof(double);
     if (!workspace) return fail(MPCF_EINVAL, "the strided entry needs a caller workspace (mpcf_step_rk4_jvp_workspace_bytes)");
     if (reinterpret_cast<uintptr_t>(workspace) % 128) return fail(MPCF_EINVAL, "workspace must be 128-byte aligned");
     if (workspace_bytes < min_ws) return fail(MPCF_EINVAL, "workspace too small: see mpcf_step_rk4_jvp_workspace_bytes");

@@ -30,7 +30,7 @@
 namespace mpcf {
 
 // spatial motion x motion
-MPCF_DI void mxm(const double *a, const double *b, double *o)
+MPCF_HD void mxm(const double *a, const double *b, double *o)
 {
     double t0[3], t1[3];
     cross3(a + 3, b, t0);
@@ -39,7 +39,7 @@ MPCF_DI void mxm(const double *a, const double *b, double *o)
     o[0] = t0[0] + t1[0]; o[1] = t0[1] + t1[1]; o[2] = t0[2] + t1[2];
 }
 // spatial motion x* force
-MPCF_DI void mxf(const double *a, const double *f, double *o)
+MPCF_HD void mxf(const double *a, const double *f, double *o)
 {
     double t0[3], t1[3];
     cross3(a + 3, f, o);
@@ -49,17 +49,17 @@ MPCF_DI void mxf(const double *a, const double *f, double *o)
 }
 // one out-of-line copy of sincos (its large-argument slow path is ~150 instructions per inlined call site; the derivative
 // kernels are instruction-fetch bound at 110 KB of straight-line code)
-__device__ __noinline__ void sincos_shared(double x, double *s, double *c) { sincos(x, s, c); }
+static __device__ __noinline__ void sincos_shared(double x, double *s, double *c) { sincos(x, s, c); }
 
-MPCF_DI double dot6(const double *a, const double *b)
+MPCF_HD double dot6(const double *a, const double *b)
 {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
-MPCF_DI double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+MPCF_HD double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 struct RigidInertiaW {  // rigid-body inertia about the world origin, world axes
     double m, h[3], Io[6];
-    MPCF_DI void apply(const double *x, double *f) const
+    MPCF_HD void apply(const double *x, double *f) const
     {
         double t[3], u[3];
         cross3(h, x + 3, t);
@@ -113,7 +113,7 @@ struct FdDerivs {
 
     // world-frame rigid inertia I of link i (about the world origin), momentum H = I v, net force F = I a + v x* H and the
     // symmetric Bs of the header comment, from the link's world pose (R, o) and spatial velocity / acceleration (v, a)
-    static MPCF_DI void link_world(const MP &m, int i, const double *R, const double *o, const double *v, const double *a,
+    static MPCF_HD void link_world(const MP &m, int i, const double *R, const double *o, const double *v, const double *a,
                                    RigidInertiaW &I, double *H, double *F, double *Bsi)
     {
         const double ms = m.mass(i);
@@ -174,7 +174,7 @@ struct FdDerivs {
     }
 
     // g_k, gv_k, r_k, s_k of the pairing pass from the composites of the sub-chain rooted at k
-    static MPCF_DI void pair_vectors(const RigidInertiaW &Ic, const double *Hc, const double *Fc, const double *Bc, const LinkFwd &Kk,
+    static MPCF_HD void pair_vectors(const RigidInertiaW &Ic, const double *Hc, const double *Fc, const double *Bc, const LinkFwd &Kk,
                                      double *rk, double *sk, double *gk, double *gvk)
     {
         const double *Sk = Kk.S;

@@ -16,6 +16,9 @@
 namespace mpcf {
 
 #define MPCF_DI __device__ __forceinline__
+// pure arithmetic shared with the host-side unit checks of the run-time-tree pipeline (tests/hostcheck): same source, compiled
+// for the device in the product and, by the tests only, for the host
+#define MPCF_HD __host__ __device__ __forceinline__
 
 // ---------------------------------------------------------------------------------------------
 // Dual numbers (one tangent direction)
@@ -60,7 +63,7 @@ MPCF_DI double tangent_of(Dual a) { return a.d; }
 // small vector helpers (T or double operands mix freely through the overloads above)
 // ---------------------------------------------------------------------------------------------
 template <class A, class B, class O>
-MPCF_DI void cross3(const A *a, const B *b, O *o)
+MPCF_HD void cross3(const A *a, const B *b, O *o)
 {
     O x = a[1] * b[2] - a[2] * b[1];
     O y = a[2] * b[0] - a[0] * b[2];

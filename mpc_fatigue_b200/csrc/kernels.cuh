@@ -19,15 +19,17 @@ struct StaticParams {
 
 // ---- run-time topology: model blob staged into shared memory by every block ----
 // blob layout (doubles): Rp 9n | pp 3n | mass n | mc 3n | Io 6n | arm n | fat 4n | grav 3
-// followed by ints: parent n | jtype n | keep n  (keep[i] = 1 when some link other than i + 1 has parent i, i.e. link i's
-// kinematic state must outlive the next link of the sweep)
+// followed by ints: parent n | jtype n | keep n | depth n | rowptr n + 1  (keep[i] = 1 when some link other than i + 1 has
+// parent i, i.e. link i's kinematic state must outlive the next link of the sweep; depth / rowptr: packed ancestor storage of
+// the tree Jacobian pipeline, rowptr[i] = sum of (depth[k] + 1) over k < i)
 struct GenericBlob {
     const double *dbl;  // device
     const int *ints;    // device
     int n;
 };
 inline size_t blob_doubles(int n) { return (size_t)27 * n + 3; }
-inline size_t blob_smem_bytes(int n) { return blob_doubles(n) * sizeof(double) + (size_t)3 * n * sizeof(int); }
+inline __host__ __device__ int blob_ints(int n) { return 5 * n + 1; }
+inline size_t blob_smem_bytes(int n) { return blob_doubles(n) * sizeof(double) + (size_t)blob_ints(n) * sizeof(int); }
 
 struct FrameArg {
     int joint;  // parent joint, -1 = world
@@ -103,6 +105,12 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
                                double *M, cudaStream_t s);
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
                              double *C, cudaStream_t s);
+// analytic Jacobian pipeline for run-time trees (kernels_tree.cu): n <= 40; npat = size of the ancestor pattern
+bool tree_jvp_supported(const LaunchModel &m);
+size_t tree_jvp_workspace_bytes(int n, int npat, long U);
+cudaError_t launch_step_jvp_tree(const LaunchModel &m, int npat, long U, long cnt, const double *q, const double *qd, const double *tau,
+                                 const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, long UJ,
+                                 double *ws, size_t ws_bytes, cudaStream_t s);
 void jvp_profile_enable(bool on);
 int jvp_profile_read(double *ms3, long *launches);
 cudaError_t launch_fp64_probe(long iters, int blocks, double *out, cudaStream_t s);

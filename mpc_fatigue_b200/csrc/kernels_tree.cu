@@ -1,0 +1,471 @@
+// kernels_tree.cu — analytic Jacobian pipeline of the RK4 dynamics+fatigue step for RUN-TIME TREES (branched models with
+// revolute / prismatic joints, n <= 40: config C4's 37-joint tree), replacing the 3n + 1 dual-number sweeps for these models.
+// Same mathematics as the static-chain pipeline (kernels_jvp2.cu) with ancestor relations instead of chain
+// relations (tree_derivs.cuh), and a different chain-rule mapping, because at n = 37 the per-unit products are real matrix
+// products ([37 x 74] . [74 x 112] per stage) and the per-unit matrices do not fit a thread:
+//
+//   T1 k_tree_stages  thread = unit           primal RK4 (ABA), per stage (q_s, qd_s, qdd_s) and the fatigue-row coefficients
+//   T2 k_tree_derivs  thread = (unit, stage)  dID/dq, dID/dqd on the ancestor pattern + M = L^T D L factorised in place
+//                                             (packed: 5 npat values per stage instead of 3 n^2)
+//   T3 k_tree_chain   CTA = unit, thread = Jacobian column (3n + 1 <= 128): per stage
+//                       Z = dID/dq X[q] + dID/dqd X[qd]      rows in registers, matrices broadcast from shared memory
+//                       K = -M^-1 (Z - E_tau)                dense triangular solves with L, D in registers (unrolled)
+//                     X lives in shared memory (column-private), the packed stage data are expanded into dense
+//                     column-major matrices by cp.async scatter copies that run one stage ahead of the arithmetic.
+//
+// Accumulator identities that keep the per-thread state at two register arrays (acc, P) — checked on the host by
+// tests/hostcheck (same formulas as plain loops) and on the GPU against the oracle:
+//   Yv_s = h K_s (+ qdd_s in the dt column),  P = Yv_1 + Yv_2 + Yv_3
+//   d q+ /dz = X1[q] + h X1[qd] + (h/6) P (+ sum_s w_s qd_s in the dt column)
+//   d qd+/dz = X1[qd] + (2 P - Yv_1 + Yv_4) / 6          (X1[qd] - Yv_1/6 is stored after stage 1, the rest added at the end)
+//   d f+_i/dz = sum_{s<=3} fnext_s[i] Yv_s[i] (+ closed-form terms), fnext_s = c_s gamma_{s+1}(lambda_i h) (h/6) 2 kappa_i cv_i qd_{s+1,i}
+//               with gamma = (1 - z + z^2/2 - z^3/4, 2 - z + z^2/2, 2 - z, 1): the RK4 response of the linear fatigue rows
+//               to a forcing applied at stage s, so the rows need no per-column recursion state.
+#include <atomic>
+
+#include "launch.cuh"
+#include "tree_derivs.cuh"
+
+namespace mpcf {
+
+// ------------------------------------------------------------------------------------------------ workspace layout
+struct TreeWs {
+    int n, npat, NE;  // NE planes of 32 doubles per (tile, stage)
+    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n; }
+    MPCF_HD size_t chunk(long tile, int s) const { return ((size_t)tile * 4 + s) * NE * 32; }
+    // plane indices
+    MPCF_HD int dqkj(int e) const { return e; }
+    MPCF_HD int dqjk(int e) const { return npat + e; }
+    MPCF_HD int dvkj(int e) const { return 2 * npat + e; }
+    MPCF_HD int dvjk(int e) const { return 3 * npat + e; }
+    MPCF_HD int lf(int e) const { return 4 * npat + e; }
+    MPCF_HD int vec(int slot, int i) const { return 5 * npat + slot * n + i; }  // 0 qd_s, 1 qdd_s, 2 fnext_s, 3 q_s, 4 extra_s
+};
+size_t tree_ws_doubles_per_unit(int n, int npat) { return (size_t)4 * TreeWs::planes(n, npat); }
+
+// ------------------------------------------------------------------------------------------------ T1
+template <int MAXN>
+__global__ void __launch_bounds__(kThreads, 3) k_tree_stages(GenericBlob blob, TreeWs W, long U, long cnt, const double *q, const double *qd,
+                                                            const double *tau, const double *f, double dt, const double *dt_u, double *qn,
+                                                            double *qdn, double *fn, double *ws)
+{
+    extern __shared__ double smem[];
+    const int n = blob.n;
+    const int nd = 27 * n + 3;
+    int *si = reinterpret_cast<int *>(smem + nd);
+    for (int k = threadIdx.x; k < nd; k += blockDim.x) smem[k] = blob.dbl[k];
+    for (int k = threadIdx.x; k < blob_ints(n); k += blockDim.x) si[k] = blob.ints[k];
+    __syncthreads();
+    const GenericModel<MAXN> m{n, smem, si};
+    using D = Dyn<double, GenericModel<MAXN>>;
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= cnt) return;
+    double x[3 * MAXN], t[MAXN], xs[3 * MAXN], xn[3 * MAXN], k[3 * MAXN];
+    double fsum[MAXN], gdt[MAXN], qdbar[MAXN];
+    for (int i = 0; i < n; ++i) {
+        x[i] = q[i * U + u];
+        x[n + i] = qd[i * U + u];
+        x[2 * n + i] = f[i * U + u];
+        t[i] = tau[i * U + u];
+        fsum[i] = 0.0; gdt[i] = 0.0; qdbar[i] = 0.0;
+    }
+    const double h = dt_u ? dt_u[u] : dt;
+    for (int i = 0; i < 3 * n; ++i) { xs[i] = x[i]; xn[i] = x[i]; }
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+        const double cprev = s == 3 ? 1.0 : 0.5;  // c_{s-1}
+        const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
+        D::aba(m, xs, xs + n, t, k + n);
+        double *w = ws + W.chunk(u / 32, s) + (u & 31);
+        double *wprev = ws + W.chunk(u / 32, s > 0 ? s - 1 : 0) + (u & 31);
+        for (int i = 0; i < n; ++i) {
+            const double qdi = xs[n + i];
+            k[i] = qdi;
+            k[2 * n + i] = D::fatigue_rhs(m, i, xs[2 * n + i], t[i], qdi);
+            w[W.vec(0, i) * 32] = qdi;
+            w[W.vec(1, i) * 32] = k[n + i];
+            w[W.vec(3, i) * 32] = xs[i];
+            const double z = m.fat(i, 0) * h;
+            const double gam = s == 0 ? 1.0 + z * (-1.0 + z * (0.5 - 0.25 * z)) : (s == 1 ? 2.0 + z * (-1.0 + 0.5 * z) : (s == 2 ? 2.0 - z : 1.0));
+            const double fcoef = gam * (h / 6.0) * 2.0 * m.fat(i, 1) * m.fat(i, 3) * qdi;
+            fsum[i] += fcoef;
+            gdt[i] += gam * (1.0 / 6.0) * k[2 * n + i];
+            qdbar[i] += wt * qdi;
+            if (s > 0) wprev[W.vec(2, i) * 32] = fcoef * cprev;
+        }
+        const double a = h * wt, c = h * cs;
+        for (int i = 0; i < 3 * n; ++i) {
+            xn[i] += a * k[i];
+            xs[i] = x[i] + c * k[i];
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        ws[W.chunk(u / 32, 0) + (size_t)W.vec(4, i) * 32 + (u & 31)] = gdt[i];
+        ws[W.chunk(u / 32, 1) + (size_t)W.vec(4, i) * 32 + (u & 31)] = fsum[i];
+        ws[W.chunk(u / 32, 3) + (size_t)W.vec(4, i) * 32 + (u & 31)] = qdbar[i];
+        if (qn) {
+            qn[i * U + u] = xn[i];
+            qdn[i * U + u] = xn[n + i];
+            fn[i * U + u] = xn[2 * n + i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ T2
+struct TreePackedOut {
+    double *o;  // this lane's element of plane 0 of the (tile, stage) chunk
+    TreeWs W;
+    MPCF_HD void pair(int, int, int e, double dqkj, double dvkj, double dqjk, double dvjk) const
+    {
+        o[(size_t)W.dqkj(e) * 32] = dqkj;
+        o[(size_t)W.dqjk(e) * 32] = dqjk;
+        o[(size_t)W.dvkj(e) * 32] = dvkj;
+        o[(size_t)W.dvjk(e) * 32] = dvjk;
+    }
+};
+
+template <int MAXN>
+__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws)
+{
+    extern __shared__ double smem[];
+    const int n = blob.n;
+    const int nd = 27 * n + 3;
+    int *si = reinterpret_cast<int *>(smem + nd);
+    for (int k = threadIdx.x; k < nd; k += blockDim.x) smem[k] = blob.dbl[k];
+    for (int k = threadIdx.x; k < blob_ints(n); k += blockDim.x) si[k] = blob.ints[k];
+    __syncthreads();
+    const GenericModel<MAXN> m{n, smem, si};
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= cnt) return;
+    const int s = blockIdx.y;
+    double *o = ws + W.chunk(u / 32, s) + (u & 31);
+    double q[MAXN], qd[MAXN], qdd[MAXN];
+    for (int i = 0; i < n; ++i) {
+        q[i] = o[(size_t)W.vec(3, i) * 32];
+        qd[i] = o[(size_t)W.vec(0, i) * 32];
+        qdd[i] = o[(size_t)W.vec(1, i) * 32];
+    }
+    TreeRec rec[MAXN];
+    TreeComp comp[MAXN];
+    double Mp[MAXN * (MAXN + 1) / 2];
+    TreePackedOut out{o, W};
+    TreeDerivs<GenericModel<MAXN>>::forward(m, q, qd, qdd, rec);
+    TreeDerivs<GenericModel<MAXN>>::backward(m, rec, comp, Mp, out);
+    TreeDerivs<GenericModel<MAXN>>::factorize(m, Mp);
+    for (int k = 0; k < n; ++k) {
+        const int e0 = m.rowptr(k), e1 = e0 + m.depth(k);  // e1 = the diagonal entry
+        for (int e = e0; e < e1; ++e) o[(size_t)W.lf(e) * 32] = Mp[e];
+        o[(size_t)W.lf(e1) * 32] = 1.0 / Mp[e1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ T3
+MPCF_DI void cp_async8s(unsigned smem_addr, const double *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+MPCF_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+MPCF_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TreeChainArgs {
+    TreeWs W;
+    long U, UJ, cnt;         // plane strides of the inputs / of jac, units in this launch
+    const double *tau, *dt_u;
+    double dt;
+    const double *ws;
+    double *jac;
+    double *scratch;         // [gridDim.x][n][128] fatigue-row accumulators (L2-resident, coalesced)
+    const double *fat;       // device blob: fat[n][4]
+    const int *ints;         // device blob ints: parent n | jtype n | keep n | depth n | rowptr n + 1
+    int fence0;              // always 0: `if (a.fence0 > i) continue;` is never taken but cuts the unrolled triangular solves into one
+                             // basic block per column (cf. StaticModel::skip); in one block ptxas hoists ~800 loads and spills 6.7 KB
+};
+
+// NR: padded row count (even, n <= NR); XS: column stride of the X arrays
+template <int NR>
+__global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
+{
+    const TreeWs W = a.W;
+    const int n = W.n, npat = W.npat;
+    const int NC = 3 * n + 1;
+    const int XS = (NC + 15) & ~15;
+    extern __shared__ __align__(16) double sm[];
+    double *DqT = sm, *DvT = DqT + n * NR, *LT = DvT + n * NR;      // column-major: column c at c * NR; LT is NR x NR (padding = 0)
+    double *V = LT + NR * NR;                                      // 2 buffers x 4 vectors x NR: qd_s, qdd_s, fnext_s, extra_s
+    double *Xq = V + 2 * 4 * NR, *Xv = Xq + n * XS;
+    unsigned short *okj = reinterpret_cast<unsigned short *>(Xv + n * XS), *ojk = okj + npat;
+    const int t = threadIdx.x;
+    const bool active = t < NC;
+    // ---- once per CTA: zero the dense matrices, build the packed-entry -> dense-offset tables ----
+    for (int i = t; i < 2 * n * NR + NR * NR; i += 128) sm[i] = 0.0;
+    for (int i = t; i < 2 * 4 * NR; i += 128) V[i] = 0.0;
+    {
+        const int *parent = a.ints, *depth = a.ints + 3 * n, *rowptr = a.ints + 4 * n;
+        for (int k = t; k < n; k += 128)
+            for (int j = k; j >= 0; j = parent[j]) {
+                const int e = rowptr[k] + depth[j];
+                okj[e] = (unsigned short)(j * NR + k);  // entry (row k, col j)
+                ojk[e] = (unsigned short)(k * NR + j);  // entry (row j, col k)
+            }
+    }
+    __syncthreads();
+    const int jq = t < n ? t : -1, jv = (t >= n && t < 2 * n) ? t - n : -1, jt = (t >= 2 * n && t < 3 * n) ? t - 2 * n : -1;
+    const bool isdt = t == 3 * n;
+    const unsigned sDq = (unsigned)__cvta_generic_to_shared(DqT), sDv = (unsigned)__cvta_generic_to_shared(DvT),
+                   sLT = (unsigned)__cvta_generic_to_shared(LT), sV = (unsigned)__cvta_generic_to_shared(V);
+    // group A of (unit u, stage s): dID/dq, dID/dqd entries + the four vectors (into vector buffer s & 1); group B: the factor
+    auto issue_A = [&](long u, int s) {
+        const double *w = a.ws + W.chunk(u / 32, s) + (u & 31);
+        for (int e = t; e < npat; e += 128) {
+            const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
+            cp_async8s(sDq + kj, w + (size_t)W.dqkj(e) * 32);
+            cp_async8s(sDv + kj, w + (size_t)W.dvkj(e) * 32);
+            if (kj != jk) {
+                cp_async8s(sDq + jk, w + (size_t)W.dqjk(e) * 32);
+                cp_async8s(sDv + jk, w + (size_t)W.dvjk(e) * 32);
+            }
+        }
+        const unsigned vb = sV + (unsigned)((s & 1) * 4 * NR) * 8u;
+        for (int i = t; i < n; i += 128) {
+            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, w + (size_t)W.vec(0, i) * 32);
+            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, w + (size_t)W.vec(1, i) * 32);
+            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, w + (size_t)W.vec(2, i) * 32);
+            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, w + (size_t)W.vec(4, i) * 32);
+        }
+        cp_async_commit();
+    };
+    auto issue_B = [&](long u, int s) {
+        const double *w = a.ws + W.chunk(u / 32, s) + (u & 31);
+        for (int e = t; e < npat; e += 128) cp_async8s(sLT + okj[e] * 8u, w + (size_t)W.lf(e) * 32);  // L_kj at (row k, col j); diagonal: 1 / D_k
+        cp_async_commit();
+    };
+    double *AF = a.scratch + (size_t)blockIdx.x * n * 128 + t;
+    long u = blockIdx.x;
+    if (u < a.cnt) { issue_A(u, 0); issue_B(u, 0); }
+    for (; u < a.cnt; u += gridDim.x) {
+        const double h = a.dt_u ? a.dt_u[u] : a.dt;
+        double acc[NR], P[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) P[r] = 0.0;
+        if (active)
+            for (int c = 0; c < n; ++c) { Xq[c * XS + t] = (c == jq) ? 1.0 : 0.0; Xv[c * XS + t] = (c == jv) ? 1.0 : 0.0; }
+        const long PC = 4 * n + 1;
+        const long ocol = isdt ? 4 * n : t;
+        double *jq_out = a.jac + (size_t)ocol * a.UJ + u;  // + row * PC * UJ
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+            const long un = u + gridDim.x;  // the item after (u, 3) is (un, 0)
+            const bool more = s < 3 || un < a.cnt;
+            const long u2 = s < 3 ? u : un;
+            const int s2 = s < 3 ? s + 1 : 0;
+            cp_async_wait<1>();  // group A of this stage has landed (B may still be in flight)
+            __syncthreads();
+            // ---- phase 1: acc = dID/dq X[q] + dID/dqd X[qd] ----
+            if (s == 0) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc[r] = jq >= 0 ? DqT[jq * NR + r] : (jv >= 0 ? DvT[jv * NR + r] : 0.0);
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc[r] = 0.0;
+                if (active) {
+#pragma unroll 1
+                    for (int c = 0; c < n; ++c) {
+                        const double xq = Xq[c * XS + t], xv = Xv[c * XS + t];
+                        const double2 *dq = reinterpret_cast<const double2 *>(DqT + c * NR);
+                        const double2 *dv = reinterpret_cast<const double2 *>(DvT + c * NR);
+                        // blocks of 8 rows with a scheduling fence in between: left alone, ptxas issues all 2 x NR / 2 broadcast
+                        // loads of a column first and spills the accumulators to make room for them
+#pragma unroll
+                        for (int b = 0; b < NR / 2; b += 4) {
+#pragma unroll
+                            for (int r2 = b; r2 < b + 4 && r2 < NR / 2; ++r2) {
+                                const double2 A = dq[r2], B = dv[r2];
+                                acc[2 * r2] = fma(A.x, xq, acc[2 * r2]);
+                                acc[2 * r2 + 1] = fma(A.y, xq, acc[2 * r2 + 1]);
+                                acc[2 * r2] = fma(B.x, xv, acc[2 * r2]);
+                                acc[2 * r2 + 1] = fma(B.y, xv, acc[2 * r2 + 1]);
+                            }
+                            if (a.fence0 > b) break;
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // every thread is done with this stage's dID/dq, dID/dqd: the next stage's may land
+            if (more) issue_A(u2, s2); else cp_async_commit();
+            cp_async_wait<1>();  // group B of this stage has landed (the A just issued may still be in flight)
+            __syncthreads();
+            // ---- phase 2: rhs = -acc (+ e_j in the tau columns); M k = rhs with M = L^T D L ----
+#pragma unroll
+            for (int r = 0; r < NR; ++r) acc[r] = ((r == jt) ? 1.0 : 0.0) - acc[r];
+#pragma unroll
+            for (int i = NR - 2; i >= 0; --i) {  // L^T y = rhs: y_i = rhs_i - sum_{k > i} L_ki y_k   (column i of L is contiguous)
+                if (a.fence0 > i) continue;
+                double s0 = 0.0, s1 = 0.0;
+                const double *col = LT + i * NR;
+                if ((i + 1) & 1) s0 = col[i + 1] * acc[i + 1];  // odd start: one scalar load, then aligned pairs (16-byte broadcasts)
+#pragma unroll
+                for (int k = (i + 2) & ~1; k < NR; k += 2) {
+                    const double2 L2 = *reinterpret_cast<const double2 *>(col + k);
+                    s0 = fma(L2.x, acc[k], s0);
+                    s1 = fma(L2.y, acc[k + 1], s1);
+                }
+                acc[i] -= s0 + s1;
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] *= LT[i * NR + i];  // 1 / D_i (0 in the padding rows)
+#pragma unroll
+            for (int j = 0; j < NR - 1; ++j) {  // L x = w, column-oriented
+                if (a.fence0 > j) continue;
+                const double *col = LT + j * NR;
+                const double xj = -acc[j];
+                if ((j + 1) & 1) acc[j + 1] = fma(col[j + 1], xj, acc[j + 1]);
+#pragma unroll
+                for (int i = (j + 2) & ~1; i < NR; i += 2) {
+                    const double2 L2 = *reinterpret_cast<const double2 *>(col + i);
+                    acc[i] = fma(L2.x, xj, acc[i]);
+                    acc[i + 1] = fma(L2.y, xj, acc[i + 1]);
+                }
+            }
+            __syncthreads();  // every thread is done with this stage's factor
+            if (more) issue_B(u2, s2); else cp_async_commit();
+            // ---- update: Yv, accumulators, next stage's X (column-private) ----
+            const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+            const double *Vs = V + (s & 1) * 4 * NR;
+            if (active) {
+                const bool rmw = s == 1 || s == 2;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if (r < n) {
+                        const double yv = h * acc[r] + (isdt ? Vs[1 * NR + r] : 0.0);
+                        acc[r] = yv;
+                        const double xvold = Xv[r * XS + t];
+                        if (s == 0) jq_out[(size_t)(n + r) * PC * a.UJ] = ((r == jv) ? 1.0 : 0.0) - yv * (1.0 / 6.0);
+                        if (s < 3) {
+                            P[r] += yv;
+                            const double fa = Vs[2 * NR + r] * yv;
+                            AF[r * 128] = rmw ? AF[r * 128] + fa : fa;
+                        }
+                        const double yq = h * xvold + (isdt ? Vs[0 * NR + r] : 0.0);
+                        Xq[r * XS + t] = ((r == jq) ? 1.0 : 0.0) + cs * yq;
+                        Xv[r * XS + t] = ((r == jv) ? 1.0 : 0.0) + cs * yv;
+                    }
+                }
+            }
+            // the extra vectors: stage 0 -> gdtsum, stage 1 -> fsum, stage 3 -> qdbar; each thread keeps the entries it needs
+            if (active) {
+                if (s == 0 && isdt) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+                        if (r < n) AF[r * 128] += Vs[3 * NR + r];  // dt column: sum_s gamma_s / 6 fdot_s
+                }
+                if (s == 1 && jv >= 0) AF[jv * 128] += Vs[3 * NR + jv];  // qd column j, row j: X1[qd] term, sum_s fcoef_s
+            }
+            if (s == 3 && active) {
+                // ---- epilogue of this column ----
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if (r < n) {
+                        const double aq = ((r == jq) ? 1.0 : 0.0) + h * ((r == jv) ? 1.0 : 0.0) + (h * (1.0 / 6.0)) * P[r] + (isdt ? Vs[3 * NR + r] : 0.0);
+                        jq_out[(size_t)r * PC * a.UJ] = aq;
+                        double *pv = jq_out + (size_t)(n + r) * PC * a.UJ;
+                        *pv += (2.0 * P[r] + acc[r]) * (1.0 / 6.0);
+                        double af = AF[r * 128];
+                        if (r == jt) {
+                            const double z = a.fat[4 * r] * h;
+                            af += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                        }
+                        jq_out[(size_t)(2 * n + r) * PC * a.UJ] = af;
+                    }
+                }
+            }
+        }
+        // ---- the n fatigue columns: closed form (d(q+, qd+)/df = 0, df+/df = diag RK4 amplification) ----
+        for (int idx = t; idx < 3 * n * n; idx += 128) {
+            const int r = idx / n, j = idx - r * n;
+            double v = 0.0;
+            if (r == 2 * n + j) {
+                const double z = a.fat[4 * j] * h;
+                v = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
+            }
+            a.jac[((size_t)r * PC + 3 * n + j) * a.UJ + u] = v;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+static std::atomic<bool> g_tree_attr[64];
+
+bool tree_jvp_supported(const LaunchModel &m) { return (m.fam == FAM_GENERIC16 || m.fam == FAM_GENERIC64) && m.n <= 40; }
+
+static size_t tree_chain_smem(int n, int NR, int npat)
+{
+    const int NC = 3 * n + 1, XS = (NC + 15) & ~15;
+    return ((size_t)2 * n * NR + (size_t)NR * NR + 2 * 4 * NR + (size_t)2 * n * XS) * sizeof(double) + (size_t)2 * npat * sizeof(unsigned short);
+}
+
+template <int MAXN, int NR>
+static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, const double *q, const double *qd, const double *tau, const double *f,
+                            double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, long UJ, double *ws, size_t ws_bytes,
+                            cudaStream_t s)
+{
+    const int n = m.n;
+    TreeWs W{n, npat, TreeWs::planes(n, npat)};
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem3 = tree_chain_smem(n, NR, npat);
+    if (dev >= 0 && dev < 64 && !g_tree_attr[dev].load(std::memory_order_acquire)) {
+        // n <= 38 fits two CTAs per SM (<= 113 KB each); n = 39, 40 run one CTA per SM
+        cudaError_t e = cudaFuncSetAttribute(k_tree_chain<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tree_chain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        if (e != cudaSuccess) return e;
+        g_tree_attr[dev].store(true, std::memory_order_release);
+    }
+    const int ctas_per_sm = smem3 <= 113 * 1024 ? 2 : 1;
+    const long grid3_max = (long)nsm * ctas_per_sm;
+    // workspace = [stage data of the chunk][fatigue-row scratch of the chain kernel's CTAs]
+    const size_t scratch_bytes = (size_t)grid3_max * n * 128 * sizeof(double);
+    if (ws_bytes <= scratch_bytes) return cudaErrorInvalidValue;
+    const size_t per_unit = tree_ws_doubles_per_unit(n, npat) * sizeof(double);
+    long Uc = (long)((ws_bytes - scratch_bytes) / per_unit);
+    Uc -= Uc % 32;
+    if (Uc < 32) return cudaErrorInvalidValue;
+    double *scratch = ws + (size_t)Uc * tree_ws_doubles_per_unit(n, npat);
+    const size_t smem12 = blob_smem_bytes(n);
+    for (long u0 = 0; u0 < cnt; u0 += Uc) {
+        const long c = (cnt - u0) < Uc ? (cnt - u0) : Uc;
+        const unsigned gb = (unsigned)((c + kThreads - 1) / kThreads);
+        k_tree_stages<MAXN><<<gb, kThreads, smem12, s>>>(m.blob, W, U, c, q + u0, qd + u0, tau + u0, f + u0, dt, dt_u ? dt_u + u0 : nullptr,
+                                                        qn ? qn + u0 : nullptr, qdn ? qdn + u0 : nullptr, fn ? fn + u0 : nullptr, ws);
+        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws);
+        TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
+        const unsigned g3 = (unsigned)(c < grid3_max ? c : grid3_max);
+        k_tree_chain<NR><<<g3, 128, smem3, s>>>(a);
+        g_launches.fetch_add(3);
+    }
+    return cudaGetLastError();
+}
+
+size_t tree_jvp_workspace_bytes(int n, int npat, long U)
+{
+    long units = U < (1L << 15) ? U : (1L << 15);  // chunks of at most 32768 units (1.9 GB for the 37-joint tree)
+    units = (units + 31) / 32 * 32;
+    const size_t scratch = (size_t)148 * 4 * n * 128 * sizeof(double) * 2;  // generous: up to 2x the CTAs of a 148-SM part
+    return (size_t)units * tree_ws_doubles_per_unit(n, npat) * sizeof(double) + scratch;
+}
+
+cudaError_t launch_step_jvp_tree(const LaunchModel &m, int npat, long U, long cnt, const double *q, const double *qd, const double *tau,
+                                 const double *f, double dt, const double *dt_u, double *qn, double *qdn, double *fn, double *jac, long UJ,
+                                 double *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (cnt <= 0) return cudaSuccess;
+    if (m.n <= 16) return run_tree<16, 16>(m, npat, U, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, ws_bytes, s);
+    if (m.n <= 40) return run_tree<40, 40>(m, npat, U, cnt, q, qd, tau, f, dt, dt_u, qn, qdn, fn, jac, UJ, ws, ws_bytes, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace mpcf

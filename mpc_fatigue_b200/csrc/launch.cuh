@@ -52,19 +52,23 @@ struct GenericModel {
     int n_;
     const double *d;  // shared memory
     const int *ii;    // shared memory
-    MPCF_DI int n() const { return n_; }
-    MPCF_DI int parent(int i) const { return ii[i]; }
-    MPCF_DI bool prismatic(int i) const { return ii[n_ + i] != 0; }
-    MPCF_DI bool keep(int i) const { return ii[2 * n_ + i] != 0; }
-    MPCF_DI double Rp(int i, int k) const { return d[9 * i + k]; }
-    MPCF_DI double pp(int i, int k) const { return d[9 * n_ + 3 * i + k]; }
-    MPCF_DI double mass(int i) const { return d[12 * n_ + i]; }
-    MPCF_DI double mc(int i, int k) const { return d[13 * n_ + 3 * i + k]; }
-    MPCF_DI double Io(int i, int k) const { return d[16 * n_ + 6 * i + k]; }
-    MPCF_DI double arm(int i) const { return d[22 * n_ + i]; }
-    MPCF_DI double fat(int i, int k) const { return d[23 * n_ + 4 * i + k]; }
-    MPCF_DI double grav(int k) const { return d[27 * n_ + k]; }
-    MPCF_DI bool skip(int) const { return false; }
+    MPCF_HD int n() const { return n_; }
+    MPCF_HD int parent(int i) const { return ii[i]; }
+    MPCF_HD bool prismatic(int i) const { return ii[n_ + i] != 0; }
+    MPCF_HD bool keep(int i) const { return ii[2 * n_ + i] != 0; }
+    // depth of link i (roots: 0) and the offset of its row in the packed ancestor storage of the tree pipeline: entry (i, j), j an
+    // ancestor of i or i itself, lives at rowptr(i) + depth(j)
+    MPCF_HD int depth(int i) const { return ii[3 * n_ + i]; }
+    MPCF_HD int rowptr(int i) const { return ii[4 * n_ + i]; }
+    MPCF_HD double Rp(int i, int k) const { return d[9 * i + k]; }
+    MPCF_HD double pp(int i, int k) const { return d[9 * n_ + 3 * i + k]; }
+    MPCF_HD double mass(int i) const { return d[12 * n_ + i]; }
+    MPCF_HD double mc(int i, int k) const { return d[13 * n_ + 3 * i + k]; }
+    MPCF_HD double Io(int i, int k) const { return d[16 * n_ + 6 * i + k]; }
+    MPCF_HD double arm(int i) const { return d[22 * n_ + i]; }
+    MPCF_HD double fat(int i, int k) const { return d[23 * n_ + 4 * i + k]; }
+    MPCF_HD double grav(int k) const { return d[27 * n_ + k]; }
+    MPCF_HD bool skip(int) const { return false; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, GenericMinBlocks<Body>::value) gener
     const int nd = 27 * n + 3;
     int *si = reinterpret_cast<int *>(smem + nd);
     for (int k = threadIdx.x; k < nd; k += blockDim.x) smem[k] = blob.dbl[k];
-    for (int k = threadIdx.x; k < 3 * n; k += blockDim.x) si[k] = blob.ints[k];
+    for (int k = threadIdx.x; k < blob_ints(n); k += blockDim.x) si[k] = blob.ints[k];
     __syncthreads();
     const GenericModel<MAXN> m{n, smem, si};
     const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
