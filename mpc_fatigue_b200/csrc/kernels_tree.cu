@@ -13,8 +13,10 @@
 //                     X lives in shared memory (column-private), the packed stage data are expanded into dense
 //                     column-major matrices by cp.async scatter copies that run one stage ahead of the arithmetic.
 //
-// Accumulator identities that keep the per-thread state at two register arrays (acc, P) — checked on the host by
-// tests/hostcheck (same formulas as plain loops) and on the GPU against the oracle:
+// Accumulator identities that keep the per-thread register state at ONE array (acc): P and the fatigue-row sums live in a
+// per-CTA scratch in global memory ([row][128 columns]: coalesced, L2-resident) and are updated with fire-and-forget
+// red.global.add, so no stage waits for a load — checked on the host by tests/hostcheck (same formulas as plain loops) and on
+// the GPU against the oracle:
 //   Yv_s = h K_s (+ qdd_s in the dt column),  P = Yv_1 + Yv_2 + Yv_3
 //   d q+ /dz = X1[q] + h X1[qd] + (h/6) P (+ sum_s w_s qd_s in the dt column)
 //   d qd+/dz = X1[qd] + (2 P - Yv_1 + Yv_4) / 6          (X1[qd] - Yv_1/6 is stored after stage 1, the rest added at the end)
@@ -176,7 +178,7 @@ struct TreeChainArgs {
     double dt;
     const double *ws;
     double *jac;
-    double *scratch;         // [gridDim.x][n][128] fatigue-row accumulators (L2-resident, coalesced)
+    double *scratch;         // [gridDim.x][2][n][128]: fatigue-row sums and P per column (L2-resident, coalesced)
     const double *fat;       // device blob: fat[n][4]
     const int *ints;         // device blob ints: parent n | jtype n | keep n | depth n | rowptr n + 1
     int fence0;              // always 0: `if (a.fence0 > i) continue;` is never taken but cuts the unrolled triangular solves into one
@@ -241,14 +243,12 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
         for (int e = t; e < npat; e += 128) cp_async8s(sLT + okj[e] * 8u, w + (size_t)W.lf(e) * 32);  // L_kj at (row k, col j); diagonal: 1 / D_k
         cp_async_commit();
     };
-    double *AF = a.scratch + (size_t)blockIdx.x * n * 128 + t;
+    double *AF = a.scratch + (size_t)blockIdx.x * 2 * n * 128 + t, *Ps = AF + (size_t)n * 128;
     long u = blockIdx.x;
     if (u < a.cnt) { issue_A(u, 0); issue_B(u, 0); }
     for (; u < a.cnt; u += gridDim.x) {
         const double h = a.dt_u ? a.dt_u[u] : a.dt;
-        double acc[NR], P[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) P[r] = 0.0;
+        double acc[NR];
         if (active)
             for (int c = 0; c < n; ++c) { Xq[c * XS + t] = (c == jq) ? 1.0 : 0.0; Xv[c * XS + t] = (c == jv) ? 1.0 : 0.0; }
         const long PC = 4 * n + 1;
@@ -275,17 +275,21 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
                         const double xq = Xq[c * XS + t], xv = Xv[c * XS + t];
                         const double2 *dq = reinterpret_cast<const double2 *>(DqT + c * NR);
                         const double2 *dv = reinterpret_cast<const double2 *>(DvT + c * NR);
-                        // blocks of 8 rows with a scheduling fence in between: left alone, ptxas issues all 2 x NR / 2 broadcast
-                        // loads of a column first and spills the accumulators to make room for them
+                        // two half-columns: all broadcast loads of a half first (80 staging registers), then its FMAs.  Left to
+                        // itself ptxas funnels every load through one register and each DFMA waits for its own LDS; the never-taken
+                        // branch keeps the halves in separate basic blocks so the loads are not sunk back into the FMA stream
 #pragma unroll
-                        for (int b = 0; b < NR / 2; b += 4) {
+                        for (int b = 0; b < NR / 2; b += NR / 4) {
+                            double2 A[NR / 4], B[NR / 4];
 #pragma unroll
-                            for (int r2 = b; r2 < b + 4 && r2 < NR / 2; ++r2) {
-                                const double2 A = dq[r2], B = dv[r2];
-                                acc[2 * r2] = fma(A.x, xq, acc[2 * r2]);
-                                acc[2 * r2 + 1] = fma(A.y, xq, acc[2 * r2 + 1]);
-                                acc[2 * r2] = fma(B.x, xv, acc[2 * r2]);
-                                acc[2 * r2 + 1] = fma(B.y, xv, acc[2 * r2 + 1]);
+                            for (int i = 0; i < NR / 4; ++i) { A[i] = dq[b + i]; B[i] = dv[b + i]; }
+#pragma unroll
+                            for (int i = 0; i < NR / 4; ++i) {
+                                const int r2 = b + i;
+                                acc[2 * r2] = fma(A[i].x, xq, acc[2 * r2]);
+                                acc[2 * r2 + 1] = fma(A[i].y, xq, acc[2 * r2 + 1]);
+                                acc[2 * r2] = fma(B[i].x, xv, acc[2 * r2]);
+                                acc[2 * r2 + 1] = fma(B[i].y, xv, acc[2 * r2 + 1]);
                             }
                             if (a.fence0 > b) break;
                         }
@@ -302,16 +306,20 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
 #pragma unroll
             for (int i = NR - 2; i >= 0; --i) {  // L^T y = rhs: y_i = rhs_i - sum_{k > i} L_ki y_k   (column i of L is contiguous)
                 if (a.fence0 > i) continue;
-                double s0 = 0.0, s1 = 0.0;
                 const double *col = LT + i * NR;
-                if ((i + 1) & 1) s0 = col[i + 1] * acc[i + 1];  // odd start: one scalar load, then aligned pairs (16-byte broadcasts)
+                constexpr int kMaxPairs = NR / 2;
+                double2 Lc[kMaxPairs];
+                const int k0 = (i + 2) & ~1;  // first aligned pair; an odd start contributes one scalar term
+                double s0 = ((i + 1) & 1) ? col[i + 1] * acc[i + 1] : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-                for (int k = (i + 2) & ~1; k < NR; k += 2) {
-                    const double2 L2 = *reinterpret_cast<const double2 *>(col + k);
-                    s0 = fma(L2.x, acc[k], s0);
-                    s1 = fma(L2.y, acc[k + 1], s1);
+                for (int k = k0; k < NR; k += 2) Lc[(k - k0) / 2] = *reinterpret_cast<const double2 *>(col + k);
+#pragma unroll
+                for (int k = k0; k < NR; k += 2) {
+                    const double2 L2 = Lc[(k - k0) / 2];
+                    if (((k - k0) / 2) & 1) { s2 = fma(L2.x, acc[k], s2); s3 = fma(L2.y, acc[k + 1], s3); }
+                    else { s0 = fma(L2.x, acc[k], s0); s1 = fma(L2.y, acc[k + 1], s1); }
                 }
-                acc[i] -= s0 + s1;
+                acc[i] -= (s0 + s1) + (s2 + s3);
             }
 #pragma unroll
             for (int i = 0; i < NR; ++i) acc[i] *= LT[i * NR + i];  // 1 / D_i (0 in the padding rows)
@@ -320,32 +328,37 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
                 if (a.fence0 > j) continue;
                 const double *col = LT + j * NR;
                 const double xj = -acc[j];
+                const int i0 = (j + 2) & ~1;
+                double2 Lc[NR / 2];
+#pragma unroll
+                for (int i = i0; i < NR; i += 2) Lc[(i - i0) / 2] = *reinterpret_cast<const double2 *>(col + i);
                 if ((j + 1) & 1) acc[j + 1] = fma(col[j + 1], xj, acc[j + 1]);
 #pragma unroll
-                for (int i = (j + 2) & ~1; i < NR; i += 2) {
-                    const double2 L2 = *reinterpret_cast<const double2 *>(col + i);
-                    acc[i] = fma(L2.x, xj, acc[i]);
-                    acc[i + 1] = fma(L2.y, xj, acc[i + 1]);
+                for (int i = i0; i < NR; i += 2) {
+                    acc[i] = fma(Lc[(i - i0) / 2].x, xj, acc[i]);
+                    acc[i + 1] = fma(Lc[(i - i0) / 2].y, xj, acc[i + 1]);
                 }
             }
             __syncthreads();  // every thread is done with this stage's factor
             if (more) issue_B(u2, s2); else cp_async_commit();
-            // ---- update: Yv, accumulators, next stage's X (column-private) ----
+            // ---- update: Yv, accumulators (scratch, fire-and-forget), next stage's X (column-private) ----
             const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
             const double *Vs = V + (s & 1) * 4 * NR;
             if (active) {
-                const bool rmw = s == 1 || s == 2;
 #pragma unroll
                 for (int r = 0; r < NR; ++r) {
                     if (r < n) {
                         const double yv = h * acc[r] + (isdt ? Vs[1 * NR + r] : 0.0);
                         acc[r] = yv;
                         const double xvold = Xv[r * XS + t];
-                        if (s == 0) jq_out[(size_t)(n + r) * PC * a.UJ] = ((r == jv) ? 1.0 : 0.0) - yv * (1.0 / 6.0);
-                        if (s < 3) {
-                            P[r] += yv;
-                            const double fa = Vs[2 * NR + r] * yv;
-                            AF[r * 128] = rmw ? AF[r * 128] + fa : fa;
+                        if (s == 0) {
+                            jq_out[(size_t)(n + r) * PC * a.UJ] = ((r == jv) ? 1.0 : 0.0) - yv * (1.0 / 6.0);
+                            Ps[r * 128] = yv;
+                            AF[r * 128] = Vs[2 * NR + r] * yv + (isdt ? Vs[3 * NR + r] : 0.0);  // dt column: + sum_s gamma_s / 6 fdot_s
+                        } else if (s < 3) {
+                            atomicAdd(Ps + r * 128, yv);
+                            // qd column j, row j: the X1[qd] term sum_s fcoef_s travels with stage 1
+                            atomicAdd(AF + r * 128, Vs[2 * NR + r] * yv + ((s == 1 && r == jv) ? Vs[3 * NR + r] : 0.0));
                         }
                         const double yq = h * xvold + (isdt ? Vs[0 * NR + r] : 0.0);
                         Xq[r * XS + t] = ((r == jq) ? 1.0 : 0.0) + cs * yq;
@@ -353,31 +366,32 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
                     }
                 }
             }
-            // the extra vectors: stage 0 -> gdtsum, stage 1 -> fsum, stage 3 -> qdbar; each thread keeps the entries it needs
-            if (active) {
-                if (s == 0 && isdt) {
-#pragma unroll
-                    for (int r = 0; r < NR; ++r)
-                        if (r < n) AF[r * 128] += Vs[3 * NR + r];  // dt column: sum_s gamma_s / 6 fdot_s
-                }
-                if (s == 1 && jv >= 0) AF[jv * 128] += Vs[3 * NR + jv];  // qd column j, row j: X1[qd] term, sum_s fcoef_s
-            }
             if (s == 3 && active) {
-                // ---- epilogue of this column ----
+                // ---- epilogue of this column, in four row blocks: a block's scratch loads first (independent, one round trip),
+                // then its stores.  (All rows at once would need 240 registers here, and a kernel whose first schedule does not fit
+                // the register file makes ptxas re-schedule EVERY region for minimum pressure: each DFMA then waits for its own LDS.)
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    if (r < n) {
-                        const double aq = ((r == jq) ? 1.0 : 0.0) + h * ((r == jv) ? 1.0 : 0.0) + (h * (1.0 / 6.0)) * P[r] + (isdt ? Vs[3 * NR + r] : 0.0);
-                        jq_out[(size_t)r * PC * a.UJ] = aq;
-                        double *pv = jq_out + (size_t)(n + r) * PC * a.UJ;
-                        *pv += (2.0 * P[r] + acc[r]) * (1.0 / 6.0);
-                        double af = AF[r * 128];
-                        if (r == jt) {
-                            const double z = a.fat[4 * r] * h;
-                            af += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                for (int b = 0; b < NR; b += NR / 4) {
+                    double Pv[NR / 4], Av[NR / 4];
+#pragma unroll
+                    for (int i = 0; i < NR / 4; ++i)
+                        if (b + i < n) { Pv[i] = Ps[(b + i) * 128]; Av[i] = AF[(b + i) * 128]; }
+#pragma unroll
+                    for (int i = 0; i < NR / 4; ++i) {
+                        const int r = b + i;
+                        if (r < n) {
+                            const double aq = ((r == jq) ? 1.0 : 0.0) + h * ((r == jv) ? 1.0 : 0.0) + (h * (1.0 / 6.0)) * Pv[i] + (isdt ? Vs[3 * NR + r] : 0.0);
+                            jq_out[(size_t)r * PC * a.UJ] = aq;
+                            atomicAdd(jq_out + (size_t)(n + r) * PC * a.UJ, (2.0 * Pv[i] + acc[r]) * (1.0 / 6.0));
+                            double af = Av[i];
+                            if (r == jt) {
+                                const double z = a.fat[4 * r] * h;
+                                af += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                            }
+                            jq_out[(size_t)(2 * n + r) * PC * a.UJ] = af;
                         }
-                        jq_out[(size_t)(2 * n + r) * PC * a.UJ] = af;
                     }
+                    if (a.fence0 > b) break;
                 }
             }
         }
@@ -428,7 +442,7 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
     const int ctas_per_sm = smem3 <= 113 * 1024 ? 2 : 1;
     const long grid3_max = (long)nsm * ctas_per_sm;
     // workspace = [stage data of the chunk][fatigue-row scratch of the chain kernel's CTAs]
-    const size_t scratch_bytes = (size_t)grid3_max * n * 128 * sizeof(double);
+    const size_t scratch_bytes = (size_t)grid3_max * 2 * n * 128 * sizeof(double);
     if (ws_bytes <= scratch_bytes) return cudaErrorInvalidValue;
     const size_t per_unit = tree_ws_doubles_per_unit(n, npat) * sizeof(double);
     long Uc = (long)((ws_bytes - scratch_bytes) / per_unit);
@@ -454,7 +468,7 @@ size_t tree_jvp_workspace_bytes(int n, int npat, long U)
 {
     long units = U < (1L << 15) ? U : (1L << 15);  // chunks of at most 32768 units (1.9 GB for the 37-joint tree)
     units = (units + 31) / 32 * 32;
-    const size_t scratch = (size_t)148 * 4 * n * 128 * sizeof(double) * 2;  // generous: up to 2x the CTAs of a 148-SM part
+    const size_t scratch = (size_t)148 * 4 * 2 * n * 128 * sizeof(double);  // generous: up to 2x the CTAs of a 148-SM part
     return (size_t)units * tree_ws_doubles_per_unit(n, npat) * sizeof(double) + scratch;
 }
 
