@@ -212,6 +212,35 @@ int mpcf_cost_residual_table_batch(const mpcf_model *model, long B, int N, const
                                    const double *fn, double w_qd, double w_tau, const double *bound_table,
                                    double f_max, double *out, long ld_out, void *stream);
 
+/* Fused reference-mode OCP node rows: every constraint row and the running cost the reference's scripts build per shooting
+   node, one launch for B scenarios x N nodes (node-major units u = k*B + b).  Compile-time families only.
+   One arm (chain3/6/7; python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:130-177), 3 + 3n rows:
+     [0,3) ee_pos - p_ref | n: tau = ID(q,qd,0) + wsign J^T [F;0] | n: q + h qd - q_next | n: T+ - T_next (thermal ZOH)
+     cost = w_F F.F + w_qd qd.qd                                                   (w_F = -1: the script's -F^T F)
+   Two arms (forest12x6 / forest14x7; Box_Pilz_6DOF2.py:244-293,454-475, mpc_principal.py:229-327,
+   RepeatedMPCwithThermal_confriction.py:251-273), 26 + 3n rows:
+     [0,3) F_L + F_R - fdes | [3,6) (pL-pR) x F_L + (pR-pL) x F_R | [6] |pL-pR|^2 - dist2_ref |
+     [7,10) R_L^T (pR-pL) - (the same at the previous node | rel_pos0 at node 0) | [10,13) e(R_L R_R^T) - rel_ori0 |
+     [13,23) friction cones A1 (-R_L^T F_L), A2 (-R_R^T F_R) (<= 0) | [23,26) (pL+pR)/2 - p_ref | tau | q defect | T defect
+     cost = w_box |p_box - p_ref|^2 + w_qd qd.qd + w_F (F_L.F_L + F_R.F_R)
+   Arrays: q, qd [n][U]; F [3 arms][U]; T [n][U] or NULL (thermal rows = 0); q_last / T_last [n][B]: the trailing state the
+   last node's defects compare with (NULL: zero defect there); rel_pos0 / rel_ori0 [3][B] (two arms; NULL = 0);
+   rows [rows][U], cost [U].  Optional derivative outputs (NULL to skip): dtau_dF [n][3 arms][U] = wsign J_lin^T,
+   dT_dtau [n][U] = d T+ / d tau (chain it with mpcf_node_eval_ref_jvp_batch for the thermal rows), kin_jac
+   [26 | 3][n + 3 arms][U] = d (kinematic rows) / d (q, F) of the node's own variables (the relative-position row's block
+   with respect to the previous node's q is minus the same block evaluated there). */
+typedef struct {
+    int ee_frame[2];
+    double wsign;      /* -1: force exerted ON the robot (Pilz scripts), +1: force the robot exerts (Centauro scripts) */
+    double fdes[3];    /* e.g. (0, 0, m g) */
+    double dist2_ref, mu, p_ref[3], w_box, w_qd, w_F, h;
+} mpcf_rows_opts;
+int mpcf_ocp_rows_count(const mpcf_model *model);
+int mpcf_ocp_rows_batch(const mpcf_model *model, const mpcf_rows_opts *opts, long B, int N, const double *q,
+                        const double *qd, const double *F, const double *T, const double *q_last, const double *T_last,
+                        const double *rel_pos0, const double *rel_ori0, double *rows, double *cost, double *dtau_dF,
+                        double *dT_dtau, double *kin_jac, void *stream);
+
 /* FP64-pipe probe for the roofline denominator: every thread of `blocks` x 256 runs 8 independent DFMA
    chains for `iters` iterations and writes one double to out[blocks*256] (device).
    flops = blocks * 256 * iters * 16.  Time it with events on `stream`. */

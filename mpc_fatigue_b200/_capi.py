@@ -32,6 +32,11 @@ class Coupling(C.Structure):
     _fields_ = [("ee_frame", C.c_int * 2), ("weight", C.c_double)]
 
 
+class RowsOpts(C.Structure):
+    _fields_ = [("ee_frame", C.c_int * 2), ("wsign", C.c_double), ("fdes", C.c_double * 3), ("dist2_ref", C.c_double), ("mu", C.c_double),
+                ("p_ref", C.c_double * 3), ("w_box", C.c_double), ("w_qd", C.c_double), ("w_F", C.c_double), ("h", C.c_double)]
+
+
 _dp = C.c_void_p  # device pointers travel as integers
 _sig = {
     "mpcf_opts_default": (None, [C.POINTER(Opts)]),
@@ -72,6 +77,8 @@ _sig = {
     "mpcf_cost_residual_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int] + [_dp] * 7 + [C.c_double] * 7 + [_dp, C.c_void_p]),
     "mpcf_cost_residual_table_batch": (C.c_int, [C.c_void_p, C.c_long, C.c_int] + [_dp] * 7 + [C.c_double] * 2 + [_dp, C.c_double, _dp, C.c_long,
                                                                                                          C.c_void_p]),
+    "mpcf_ocp_rows_count": (C.c_int, [C.c_void_p]),
+    "mpcf_ocp_rows_batch": (C.c_int, [C.c_void_p, C.POINTER(RowsOpts), C.c_long, C.c_int] + [_dp] * 13 + [C.c_void_p]),
     "mpcf_probe_fp64": (C.c_int, [C.c_long, C.c_int, _dp, C.c_void_p]),
     "mpcf_memcpy2d_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]),
     "mpcf_gather_planes": (C.c_int, [_dp, C.c_long, C.c_void_p, C.c_int, C.c_long, _dp, C.c_void_p]),

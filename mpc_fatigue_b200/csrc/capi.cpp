@@ -666,6 +666,41 @@ extern "C" int mpcf_cost_residual_table_batch(const mpcf_model *model, long B, i
                 "cost_residual_table_batch");
 }
 
+extern "C" int mpcf_ocp_rows_count(const mpcf_model *model)
+{
+    if (!model) return fail(MPCF_EINVAL, "null model");
+    const int arms = family_chains(model->fam);
+    if (arms == 0) return fail(MPCF_EINVAL, "the fused OCP rows need a compile-time family (chain3/6/7: one arm, forest12x6/14x7: two arms)");
+    return (arms == 2 ? 26 : 3) + 3 * model->h.n;
+}
+
+extern "C" int mpcf_ocp_rows_batch(const mpcf_model *model, const mpcf_rows_opts *o, long B, int N, const double *q, const double *qd,
+                                   const double *F, const double *T, const double *q_last, const double *T_last, const double *rel_pos0,
+                                   const double *rel_ori0, double *rows, double *cost, double *dtau_dF, double *dT_dtau, double *kin_jac,
+                                   void *stream)
+{
+    const long U = B * (long)N;
+    PROLOGUE(q && qd && F && rows && cost)
+    if (!o || B < 0 || N <= 0) return fail(MPCF_EINVAL, "bad options / B / N");
+    const int arms = family_chains(model->fam), L = family_chain_len(model->fam);
+    if (arms == 0) return fail(MPCF_EINVAL, "the fused OCP rows need a compile-time family (chain3/6/7: one arm, forest12x6/14x7: two arms)");
+    RowsHost h;
+    h.narm = arms; h.N = N; h.B = B;
+    for (int a = 0; a < arms; ++a) {
+        const int fr = o->ee_frame[a];
+        if (fr < 0 || fr >= (int)model->h.fparent.size()) return fail(MPCF_EFRAME, "ocp rows: end-effector frame index out of range");
+        const int j = model->h.fparent[fr];
+        if (j < a * L || j >= (a + 1) * L) return fail(MPCF_EFRAME, "ocp rows: ee_frame[" + std::to_string(a) + "] is not carried by arm " + std::to_string(a));
+        h.ee_joint[a] = j - a * L;
+        std::memcpy(h.ee_p[a], &model->h.fp[3 * fr], 3 * sizeof(double));
+        std::memcpy(h.ee_R[a], &model->h.fR[9 * fr], 9 * sizeof(double));
+    }
+    h.wsign = o->wsign; h.dist2_ref = o->dist2_ref; h.mu = o->mu; h.w_box = o->w_box; h.w_qd = o->w_qd; h.w_F = o->w_F; h.h = o->h;
+    std::memcpy(h.fdes, o->fdes, sizeof h.fdes);
+    std::memcpy(h.p_ref, o->p_ref, sizeof h.p_ref);
+    return done(launch_ocp_rows(lm, h, q, qd, F, T, q_last, T_last, rel_pos0, rel_ori0, rows, cost, dtau_dF, dT_dtau, kin_jac, st), "ocp_rows_batch");
+}
+
 extern "C" int mpcf_probe_fp64(long iters, int blocks, double *out, void *stream)
 {
     if (iters <= 0 || blocks <= 0 || !out) return fail(MPCF_EINVAL, "bad probe arguments");

@@ -105,6 +105,17 @@ cudaError_t launch_rnea_derivs(const LaunchModel &m, long U, const double *q, co
                                double *M, cudaStream_t s);
 cudaError_t launch_fd_derivs(const LaunchModel &m, long U, const double *q, const double *qd, const double *tau, double *A, double *B,
                              double *C, cudaStream_t s);
+// fused reference-mode OCP node rows (kernels_rows.cu)
+struct RowsHost {
+    int narm = 1, N = 0;
+    long B = 0;
+    int ee_joint[2] = {0, 0};
+    double ee_p[2][3] = {{0, 0, 0}, {0, 0, 0}}, ee_R[2][9] = {{1, 0, 0, 0, 1, 0, 0, 0, 1}, {1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    double wsign = -1.0, fdes[3] = {0, 0, 0}, dist2_ref = 0.0, mu = 0.0, p_ref[3] = {0, 0, 0}, w_box = 0.0, w_qd = 0.0, w_F = 0.0, h = 0.0;
+};
+cudaError_t launch_ocp_rows(const LaunchModel &m, const RowsHost &h, const double *q, const double *qd, const double *F, const double *T,
+                            const double *q_last, const double *T_last, const double *rel_pos0, const double *rel_ori0, double *rows,
+                            double *cost, double *dtau_dF, double *dT_dtau, double *kin_jac, cudaStream_t s);
 // analytic Jacobian pipeline for run-time trees (kernels_tree.cu): n <= 40; npat = size of the ancestor pattern
 bool tree_jvp_supported(const LaunchModel &m);
 size_t tree_jvp_workspace_bytes(int n, int npat, long U);

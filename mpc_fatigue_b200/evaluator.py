@@ -277,3 +277,32 @@ class BatchEvaluator:
                                                                  C.c_void_p(tb.data_ptr()), float(f_max),
                                                                  C.c_void_p(out.data_ptr() + 8 * out_col0), out.shape[1], _stream()))
         return out if out.shape[1] != B else out
+
+    def ocp_rows(self, B: int, N: int, ee_frames, q, qd, F, T=None, q_last=None, T_last=None, rel_pos0=None, rel_ori0=None, *, wsign=-1.0,
+                 fdes=(0.0, 0.0, 0.0), dist2_ref=0.0, mu=0.0, p_ref=(0.0, 0.0, 0.0), w_box=0.0, w_qd=0.0, w_F=0.0, h=0.0, derivatives=False):
+        """Fused reference-mode OCP node rows (include/mpcf.h: mpcf_ocp_rows_batch): every constraint row + the running cost of
+        the reference's per-node loops in one launch.  Returns (rows [nrows, U], cost [U]) and, with derivatives=True, also
+        (dtau_dF [n, 3 arms, U], dT_dtau [n, U], kin_jac [26 | 3, n + 3 arms, U])."""
+        n, U = self.n, B * N
+        nrows = int(_capi.lib.mpcf_ocp_rows_count(self.model.handle))
+        _capi.check(nrows)
+        narm = 2 if nrows == 26 + 3 * n else 1
+        if len(ee_frames) != narm:
+            raise ValueError("this model needs %d end-effector frame(s)" % narm)
+        fr = [self.model.frame_id(f) if isinstance(f, str) else int(f) for f in ee_frames] + [0] * (2 - narm)
+        o = _capi.RowsOpts((C.c_int * 2)(*fr), float(wsign), (C.c_double * 3)(*[float(v) for v in fdes]), float(dist2_ref), float(mu),
+                           (C.c_double * 3)(*[float(v) for v in p_ref]), float(w_box), float(w_qd), float(w_F), float(h))
+        f64 = dict(dtype=torch.float64, device=self.device)
+        rows, cost = torch.empty((nrows, U), **f64), torch.empty(U, **f64)
+        kin = nrows - 3 * n
+        dF = torch.empty((n, 3 * narm, U), **f64) if derivatives else None
+        dT = torch.empty((n, U), **f64) if derivatives else None
+        kj = torch.empty((kin, n + 3 * narm, U), **f64) if derivatives else None
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        with torch.cuda.device(self.device):
+            _capi.check(_capi.lib.mpcf_ocp_rows_batch(
+                self.model.handle, C.byref(o), B, N, self._in(q, n, U, "q"), self._in(qd, n, U, "qd"), self._in(F, 3 * narm, U, "F"),
+                self._in(T, n, U, "T", True), self._in(q_last, n, B, "q_last", True), self._in(T_last, n, B, "T_last", True),
+                self._in(rel_pos0, 3, B, "rel_pos0", True), self._in(rel_ori0, 3, B, "rel_ori0", True), p(rows), p(cost), p(dF), p(dT), p(kj),
+                _stream()))
+        return (rows, cost, dF, dT, kj) if derivatives else (rows, cost)

@@ -13,6 +13,8 @@ trajectories are `[B, N, n]` (scenario, node, joint) tensors on the GPU and come
   PilzForceOCP        g-rows and cost of the 6-DOF force OCP (force_optimization_pilz_6DOF.py:103-178)
   DualArmBoxOCP       g-rows of the dual-arm box OCP (Box_Pilz_6DOF2.py:217-475) and the solution.csv layout
   ThermalMPCNodes     tau / Euler / thermal-ZOH rows of the Centauro thermal MPC (mpc_principal.py:267-327)
+  FusedBoxOCP         every row + cost of the two-arm box-carrying nodes (equilibrium, relative pose, friction cones, torque,
+                      defects) from ONE fused kernel launch, with derivative blocks (mpcf_ocp_rows_batch)
 """
 from __future__ import annotations
 
@@ -121,25 +123,28 @@ class PilzForceOCP:
         self.bound = f0_bound_schedule(N, self.h, tau0, alpha, floor)
 
     def evaluate(self, q: torch.Tensor, qd: torch.Tensor, Fx: torch.Tensor, ref_xy) -> dict:
-        """q [B, N+1, 6], qd [B, N, 6], Fx [B, N] -> dict of rows."""
+        """q [B, N+1, 6], qd [B, N, 6], Fx [B, N] -> dict of rows.  ONE launch of the fused row kernel (mpcf_ocp_rows_batch):
+        torque rows, end-effector position error, Euler defects and the node cost -F^T F."""
         B, N, n = qd.shape
         ev = self.rf.ev
-        qk = q[:, :N]
-        W = torch.zeros((B, N, 6), dtype=torch.float64, device=q.device)
-        W[..., 0] = Fx
-        tau, qnext, _ = ev.node_eval_ref([self.frame], -1.0, _soa(qk), _soa(qd), _soa(W), None, self.h, want_Tnext=False)
-        pos, _ = ev.fk(self.frame, _soa(qk))
-        tau = _aos(tau, (B, N))
+        U = B * N
+        # node-major units u = k*B + b
+        nm = lambda x: x.permute(2, 1, 0).reshape(x.shape[2], -1).contiguous()
+        F = torch.zeros((3, U), dtype=torch.float64, device=q.device)
+        F[0] = Fx.t().reshape(-1)
+        rows, cost = ev.ocp_rows(B, N, [self.frame], nm(q[:, :N]), nm(qd), F, None, q[:, N].t().contiguous(), wsign=-1.0,
+                                 p_ref=(float(ref_xy[0]), float(ref_xy[1]), 0.0), w_F=-1.0, h=self.h)
+        back = lambda r: r.reshape(r.shape[0], N, B).permute(2, 1, 0)
+        tau = back(rows[3:3 + n])
         bound = torch.as_tensor(self.bound, dtype=torch.float64, device=q.device).reshape(1, N, 1)
         return {
             "tau": tau,
             "tau_bound": bound.reshape(N),
             "tau_violation": (tau.abs() - bound).clamp_min(0.0).amax(dim=(1, 2)),
-            "line": _aos(pos, (B, N))[..., :2] - torch.as_tensor(ref_xy, dtype=torch.float64, device=q.device),
-            "defect": _aos(qnext, (B, N)) - q[:, 1:],
-            "cost": -(Fx * Fx).sum(dim=1),
+            "line": back(rows[0:2]),
+            "defect": back(rows[3 + n:3 + 2 * n]),
+            "cost": cost.reshape(N, B).sum(0),
         }
-
 
     def jacobian(self, q: torch.Tensor, qd: torch.Tensor, Fx: torch.Tensor) -> dict:
         """First derivatives of the g-rows of `evaluate` with respect to the node's own decision variables
@@ -255,6 +260,42 @@ class ThermalMPCNodes:
                 "rel_pos": rel - prev,
                 "rel_ori": e - torch.as_tensor(rel_ori0, dtype=torch.float64, device=q.device).reshape(B, 1, 3),
                 "cost": cost, "pL": pL, "pR": pR}
+
+
+class FusedBoxOCP:
+    """Box-carrying node rows of the two-arm OCPs through the fused row kernel (include/mpcf.h: mpcf_ocp_rows_batch): the
+    dual Pilz box OCP on the single-tree URDF (python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:244-293,454-475) and the Centauro thermal
+    MPC node (python/Centauro_script/mpc_principal.py:229-327, friction cones of RepeatedMPCwithThermal_confriction.py:251-273):
+    force / moment equilibrium, end-effector distance, relative pose, friction cones, torque rows, Euler and thermal defects
+    and the running cost — ONE launch for all B scenarios x N nodes, plus the derivative blocks on request."""
+
+    ROWS = {"force_eq": (0, 3), "moment_eq": (3, 6), "dist2": (6, 7), "rel_pos": (7, 10), "rel_ori": (10, 13), "friction": (13, 23),
+            "box_err": (23, 26)}
+
+    def __init__(self, model: Model, ee_frames, device=None, *, wsign: float = +1.0, mass: float = 30.0, dist2_ref: float = 0.0, mu: float = 0.5,
+                 p_ref=(0.0, 0.0, 0.0), w_box: float = 1000.0, w_qd: float = 100.0, w_F: float = 10.0, T: float = 20.0, N: int = 40):
+        self.model, self.ev = model, BatchEvaluator(model, device)
+        self.frames = [model.frame_id(f) if isinstance(f, str) else int(f) for f in ee_frames]
+        self.N, self.h = N, T / N
+        self.kw = dict(wsign=wsign, fdes=(0.0, 0.0, 9.81 * mass), dist2_ref=dist2_ref, mu=mu, p_ref=tuple(p_ref), w_box=w_box, w_qd=w_qd, w_F=w_F,
+                       h=self.h)
+
+    def evaluate(self, q, qd, F_L, F_R, Temp=None, rel_pos0=None, rel_ori0=None, derivatives: bool = False) -> dict:
+        """q [B, N+1, n], qd [B, N, n], F_L / F_R [B, N, 3], Temp [B, N+1, n] or None, rel_pos0 / rel_ori0 [B, 3] or None."""
+        B, N, n = qd.shape
+        nm = lambda x: x.permute(2, 1, 0).reshape(x.shape[2], -1).contiguous()
+        tb = lambda x: None if x is None else torch.as_tensor(x, dtype=torch.float64, device=q.device).reshape(B, 3).t().contiguous()
+        F = torch.cat([nm(F_L), nm(F_R)], dim=0)
+        res = self.ev.ocp_rows(B, N, self.frames, nm(q[:, :N]), nm(qd), F, None if Temp is None else nm(Temp[:, :N]), q[:, N].t().contiguous(),
+                               None if Temp is None else Temp[:, N].t().contiguous(), tb(rel_pos0), tb(rel_ori0), derivatives=derivatives, **self.kw)
+        rows, cost = res[0], res[1]
+        back = lambda r: r.reshape(r.shape[0], N, B).permute(2, 1, 0)
+        out = {k: back(rows[a:b]) for k, (a, b) in self.ROWS.items()}
+        out.update({"tau": back(rows[26:26 + n]), "q_defect": back(rows[26 + n:26 + 2 * n]), "T_defect": back(rows[26 + 2 * n:26 + 3 * n]),
+                    "cost": cost.reshape(N, B).sum(0)})
+        if derivatives:
+            out.update({"dtau_dF": res[2], "dT_dtau": res[3], "kin_jac": res[4]})
+        return out
 
 
 def temp_simulation(Ic: float, Tin: float, T: float = 120.0, N: int = 200, Tbound: float = 70.0, ktau: float = 1.0):

@@ -508,4 +508,62 @@ static void SUF(node_eval_ref)(const mpcfo_model *m, int nee, const int *ee_fram
     }
 }
 
+/* ---- reference-mode OCP node rows (the fused kernel of csrc/kernels_rows.cu restated with the oracle's own frame FK,
+ * frame Jacobian and RNEA): one arm  python/Pilz_6_DOF/force_optimization_pilz_6DOF.py:130-177;  two arms
+ * python/2_pilz_6_DOF/Box_Pilz_6DOF2.py:244-293,454-475, python/Centauro_script/mpc_principal.py:229-327,
+ * RepeatedMPCwithThermal_confriction.py:251-273.  Row order: see include/mpcf.h (mpcf_ocp_rows_batch).
+ * qnext / Tnext: the next node's state (NULL: zero defect); relprev: R_L^T (pR - pL) at the previous node (or rel_pos0). */
+static void SUF(ocp_rows)(const mpcfo_model *m, const mpcfo_rows_opts *o, const SC *q, const SC *qd, const SC *F, const SC *T,
+                          const SC *qnext, const SC *Tnext, const SC *relprev, const double *ori0, SC *rows, SC *cost)
+{
+    int n = m->n, narm = o->narm, kin = narm == 2 ? 26 : 3;
+    SC pe[2][3], Re[2][9], W[12], zero[MAXN], Tl[MAXN], tau[MAXN], qn[MAXN], Tn[MAXN];
+    for (int i = 0; i < n; ++i) { zero[i] = 0; Tl[i] = T ? T[i] : 0; }
+    for (int c = 0; c < narm; ++c) {
+        SUF(frame_fk)(m, o->ee_frame[c], q, pe[c], Re[c]);
+        for (int k = 0; k < 3; ++k) { W[6 * c + k] = F[3 * c + k]; W[6 * c + 3 + k] = 0; }
+    }
+    SUF(node_eval_ref)(m, narm, o->ee_frame, o->wsign, q, qd, zero, W, Tl, o->h, tau, qn, Tn);
+    SC cF = 0, cqd = 0, ckin = 0;
+    for (int i = 0; i < 3 * narm; ++i) cF += F[i] * F[i];
+    for (int i = 0; i < n; ++i) {
+        cqd += qd[i] * qd[i];
+        rows[kin + i] = tau[i];
+        rows[kin + n + i] = qnext ? qn[i] - qnext[i] : 0;
+        rows[kin + 2 * n + i] = (T && Tnext) ? Tn[i] - Tnext[i] : 0;
+    }
+    if (narm == 1) {
+        for (int k = 0; k < 3; ++k) rows[k] = pe[0][k] - o->p_ref[k];
+    } else {
+        const SC *pL = pe[0], *pR = pe[1], *RL = Re[0], *RR = Re[1], *FL = F, *FR = F + 3;
+        SC d[3] = {pL[0] - pR[0], pL[1] - pR[1], pL[2] - pR[2]}, a1[3], a2[3], dm[3] = {pR[0] - pL[0], pR[1] - pL[1], pR[2] - pL[2]};
+        for (int k = 0; k < 3; ++k) rows[k] = FL[k] + FR[k] - o->fdes[k];
+        SUF(cross)(d, FL, a1);
+        SUF(cross)(dm, FR, a2);
+        for (int k = 0; k < 3; ++k) rows[3 + k] = a1[k] + a2[k];
+        rows[6] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] - o->dist2_ref;
+        SC rel[3], f1[3], f2[3], Ro[9];
+        SUF(mtv)(RL, dm, rel);
+        for (int k = 0; k < 3; ++k) rows[7 + k] = rel[k] - relprev[k];
+        SUF(mmt)(RL, RR, Ro); /* R_L R_R^T */
+        rows[10] = (Ro[7] - Ro[5]) / 2 - ori0[0];
+        rows[11] = (Ro[6] - Ro[2]) / 2 - ori0[1];
+        rows[12] = (Ro[3] - Ro[1]) / 2 - ori0[2];
+        SUF(mtv)(RL, FL, f1);
+        SUF(mtv)(RR, FR, f2);
+        for (int k = 0; k < 3; ++k) { f1[k] = -f1[k]; f2[k] = -f2[k]; }
+        const double A1[5][3] = {{0, -1, 0}, {0, -o->mu, 1}, {0, -o->mu, -1}, {1, -o->mu, 0}, {-1, -o->mu, 0}};
+        const double A2[5][3] = {{0, 1, 0}, {1, o->mu, 0}, {-1, o->mu, 0}, {0, o->mu, 1}, {0, o->mu, -1}};
+        for (int r = 0; r < 5; ++r) {
+            rows[13 + r] = A1[r][0] * f1[0] + A1[r][1] * f1[1] + A1[r][2] * f1[2];
+            rows[18 + r] = A2[r][0] * f2[0] + A2[r][1] * f2[1] + A2[r][2] * f2[2];
+        }
+        for (int k = 0; k < 3; ++k) {
+            rows[23 + k] = (pL[k] + pR[k]) / 2 - o->p_ref[k];
+            ckin += rows[23 + k] * rows[23 + k];
+        }
+    }
+    *cost = o->w_box * ckin + o->w_qd * cqd + o->w_F * cF;
+}
+
 #undef MAXN

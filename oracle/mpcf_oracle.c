@@ -254,6 +254,58 @@ int mpcfo_step_rk4_coupled_jvp_batch(const mpcfo_model *m, const mpcfo_coupling 
     return rc ? -3 : 0;
 }
 
+int mpcfo_ocp_rows_batch(const mpcfo_model *m, const mpcfo_rows_opts *o, long B, int N, const double *q, const double *qd,
+                         const double *F, const double *T, const double *q_last, const double *T_last, const double *rel_pos0,
+                         const double *rel_ori0, double *rows, double *cost, double *kin_jac)
+{
+    CHECK_N(m);
+    if (o->narm < 1 || o->narm > 2) return -2;
+    const int n = m->n, narm = o->narm, kin = narm == 2 ? 26 : 3, nrows = kin + 3 * n, nd = n + 3 * narm;
+    const long U = B * N;
+    const double hstep = 1e-40;
+#pragma omp parallel for schedule(static)
+    for (long u = 0; u < U; ++u) {
+        const long b = u % B;
+        const int k = (int)(u / B);
+        double ql[MPCFO_MAXN], qdl[MPCFO_MAXN], Tl[MPCFO_MAXN], qn[MPCFO_MAXN], Tn[MPCFO_MAXN], Fl[6], relprev[3] = {0, 0, 0}, ori0[3] = {0, 0, 0};
+        double r[26 + 3 * MPCFO_MAXN], c;
+        for (int i = 0; i < n; ++i) {
+            ql[i] = q[i * U + u]; qdl[i] = qd[i * U + u]; Tl[i] = T ? T[i * U + u] : 0.0;
+            qn[i] = k + 1 < N ? q[i * U + u + B] : (q_last ? q_last[i * B + b] : 0.0);
+            Tn[i] = T ? (k + 1 < N ? T[i * U + u + B] : (T_last ? T_last[i * B + b] : 0.0)) : 0.0;
+        }
+        for (int i = 0; i < 3 * narm; ++i) Fl[i] = F[i * U + u];
+        if (narm == 2) {
+            if (k == 0) { for (int i = 0; i < 3; ++i) relprev[i] = rel_pos0 ? rel_pos0[i * B + b] : 0.0; }
+            else {
+                double qp[MPCFO_MAXN], pL[3], RL[9], pR[3], RR[9], dm[3];
+                for (int i = 0; i < n; ++i) qp[i] = q[i * U + u - B];
+                frame_fk_r(m, o->ee_frame[0], qp, pL, RL);
+                frame_fk_r(m, o->ee_frame[1], qp, pR, RR);
+                for (int i = 0; i < 3; ++i) dm[i] = pR[i] - pL[i];
+                mtv_r(RL, dm, relprev);
+            }
+            for (int i = 0; i < 3; ++i) ori0[i] = rel_ori0 ? rel_ori0[i * B + b] : 0.0;
+        }
+        const int have_qn = k + 1 < N || q_last != NULL, have_Tn = T && (k + 1 < N || T_last != NULL);
+        ocp_rows_r(m, o, ql, qdl, Fl, T ? Tl : NULL, have_qn ? qn : NULL, have_Tn ? Tn : NULL, relprev, ori0, r, &c);
+        for (int i = 0; i < nrows; ++i) rows[i * U + u] = r[i];
+        cost[u] = c;
+        if (kin_jac) {
+            double complex qc[MPCFO_MAXN], qdc[MPCFO_MAXN], Fc[6], rc[26 + 3 * MPCFO_MAXN], cc, rp[3] = {0, 0, 0};
+            const double z3[3] = {0, 0, 0};
+            for (int d = 0; d < nd; ++d) {
+                for (int i = 0; i < n; ++i) { qc[i] = ql[i]; qdc[i] = qdl[i]; }
+                for (int i = 0; i < 3 * narm; ++i) Fc[i] = Fl[i];
+                if (d < n) qc[d] += hstep * I; else Fc[d - n] += hstep * I;
+                ocp_rows_c(m, o, qc, qdc, Fc, NULL, NULL, NULL, rp, z3, rc, &cc);
+                for (int i = 0; i < kin; ++i) kin_jac[((long)i * nd + d) * U + u] = cimag(rc[i]) / hstep;
+            }
+        }
+    }
+    return 0;
+}
+
 int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,
                             double h, double *Tnext)
 {

@@ -45,6 +45,13 @@ typedef struct {
     double weight;       /* box weight m g */
 } mpcfo_coupling;
 
+/* reference-mode OCP node rows (core.inc.h: ocp_rows; row order in include/mpcf.h: mpcf_ocp_rows_batch) */
+typedef struct {
+    int narm;
+    int ee_frame[2];
+    double wsign, fdes[3], dist2_ref, mu, p_ref[3], w_box, w_qd, w_F, h;
+} mpcfo_rows_opts;
+
 int mpcfo_set_threads(int nthreads); /* returns the thread count in use (OpenMP) */
 
 int mpcfo_rnea_batch(const mpcfo_model *m, long U, const double *q, const double *qd, const double *qdd,
@@ -71,6 +78,11 @@ int mpcfo_step_rk4_coupled_batch(const mpcfo_model *m, const mpcfo_coupling *cp,
 int mpcfo_step_rk4_coupled_jvp_batch(const mpcfo_model *m, const mpcfo_coupling *cp, long U, const double *q, const double *qd,
                                      const double *tau, const double *f, double dt, const double *dt_u, double *qn, double *qdn,
                                      double *fn, double *jac);
+
+/* rows [nrows][U], cost [U] for B scenarios x N nodes (u = k*B + b); kin_jac [26 | 3][n + 3 narm][U] by complex step */
+int mpcfo_ocp_rows_batch(const mpcfo_model *m, const mpcfo_rows_opts *o, long B, int N, const double *q, const double *qd,
+                         const double *F, const double *T, const double *q_last, const double *T_last, const double *rel_pos0,
+                         const double *rel_ori0, double *rows, double *cost, double *kin_jac);
 
 /* exact zero-order-hold fatigue/thermal map and the ODE right-hand side, element-wise per joint */
 int mpcfo_fatigue_zoh_batch(const mpcfo_model *m, long U, const double *T, const double *tau, const double *qd,

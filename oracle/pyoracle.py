@@ -180,6 +180,27 @@ class Oracle:
             raise ZeroDivisionError("ABA singular")
         return (qn, qdn, fn, J) if jac else (qn, qdn, fn)
 
+    def ocp_rows(self, opts: dict, B, N, q, qd, F, T=None, q_last=None, T_last=None, rel_pos0=None, rel_ori0=None, kin_jac=False):
+        """Reference-mode OCP node rows (core.inc.h: ocp_rows).  opts: narm, ee_frame (list), wsign, fdes, dist2_ref, mu, p_ref,
+        w_box, w_qd, w_F, h.  Returns rows [nrows, U], cost [U] (and kin_jac [kin, n + 3 narm, U] by complex step)."""
+        class _RO(C.Structure):
+            _fields_ = [("narm", C.c_int), ("ee_frame", C.c_int * 2), ("wsign", C.c_double), ("fdes", C.c_double * 3), ("dist2_ref", C.c_double),
+                        ("mu", C.c_double), ("p_ref", C.c_double * 3), ("w_box", C.c_double), ("w_qd", C.c_double), ("w_F", C.c_double), ("h", C.c_double)]
+        narm = int(opts["narm"])
+        ee = list(opts["ee_frame"]) + [0] * (2 - len(opts["ee_frame"]))
+        o = _RO(narm, (C.c_int * 2)(*ee), opts.get("wsign", -1.0), (C.c_double * 3)(*opts.get("fdes", (0, 0, 0))), opts.get("dist2_ref", 0.0),
+                opts.get("mu", 0.0), (C.c_double * 3)(*opts.get("p_ref", (0, 0, 0))), opts.get("w_box", 0.0), opts.get("w_qd", 0.0), opts.get("w_F", 0.0),
+                opts.get("h", 0.0))
+        n, U = q.shape
+        assert U == B * N
+        kin = 26 if narm == 2 else 3
+        rows, cost = np.empty((kin + 3 * n, U)), np.empty(U)
+        J = np.empty((kin, n + 3 * narm, U)) if kin_jac else None
+        rc = self.lib.mpcfo_ocp_rows_batch(self._ref(), C.byref(o), C.c_long(B), C.c_int(N), _p(_chk(q, n, U)), _p(_chk(qd, n, U)), _p(_chk(F, 3 * narm, U)),
+                                           _p(T), _p(q_last), _p(T_last), _p(rel_pos0), _p(rel_ori0), _p(rows), _p(cost), _p(J))
+        assert rc == 0, rc
+        return (rows, cost, J) if kin_jac else (rows, cost)
+
     def step_rk4_jvp_forward(self, q, qd, tau, f, dt, dt_u=None):
         """Same result as step_rk4_jvp by ONE forward-mode sweep per unit with all 3n + 1 directions in SIMD lanes
         (oracle/forward_mode.cpp, -O3 -march=native, OpenMP): the CPU baseline of bench.py.  n <= 7."""
