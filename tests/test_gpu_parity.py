@@ -60,10 +60,10 @@ def test_fk_and_jacobian_every_frame(setup):
     for fr in frames:
         pos, rot = setup["orc"].fk(fr, q)
         gpos, grot = setup["ev"].fk(fr, dq)
-        assert rel_err(gpos.cpu().numpy(), pos) < TOL and rel_err(grot.cpu().numpy(), rot) < TOL
+        assert rel_err_rows(gpos.cpu().numpy(), pos) < TOL and rel_err_rows(grot.cpu().numpy(), rot) < TOL
         J = setup["orc"].jacobian(fr, q)
         gJ = setup["ev"].jacobian(fr, dq).cpu().numpy()
-        assert rel_err(gJ, J) < TOL
+        assert rel_err_rows(gJ, J) < TOL
 
 
 def test_jac_t_wrench_and_node_eval(setup):
@@ -80,13 +80,13 @@ def test_jac_t_wrench_and_node_eval(setup):
         rt, rq, rT = setup["orc"].node_eval_ref(ee, wsign, q, qd, W, f, h, qdd=qdd)
         gt, gq, gT = setup["ev"].node_eval_ref(ee, wsign, dq, dqd, dW, df, h, qdd=dqdd)
         assert rel_err_rows(gt.cpu().numpy(), rt) < TOL
-        assert rel_err(gq.cpu().numpy(), rq) < TOL
+        assert rel_err_rows(gq.cpu().numpy(), rq) < TOL
         assert rel_err_rows(gT.cpu().numpy(), rT) < TOL
     # J^T W alone == J^T W from the materialised Jacobian of the oracle
     J = setup["orc"].jacobian(ee[0], q).reshape(6, m.n, U)
     ref = np.einsum("rnu,ru->nu", J, W[:6])
     got = setup["ev"].jac_t_wrench(ee[0], dq, dW[:6].contiguous()).cpu().numpy()
-    assert rel_err(got, ref) < TOL
+    assert rel_err_rows(got, ref) < TOL
 
 
 def test_node_eval_ref_jvp(setup):
@@ -104,8 +104,8 @@ def test_node_eval_ref_jvp(setup):
     for wsign in (-1.0, 1.0):
         rDq, rDv = setup["orc"].node_eval_ref_jvp(ee, wsign, sl(q), sl(qd), W, qdd=sl(qdd))
         gDq, gDv = setup["ev"].node_eval_ref_jvp(ee, wsign, dsl(dq), dsl(dqd), torch.from_numpy(W).cuda(), qdd=dsl(dqdd))
-        assert rel_err(gDq.cpu().numpy(), rDq) < TOL
-        assert rel_err(gDv.cpu().numpy(), rDv) < TOL
+        assert rel_err_rows(gDq.cpu().numpy(), rDq) < TOL
+        assert rel_err_rows(gDv.cpu().numpy(), rDv) < TOL
     # without wrenches it reduces to the inverse-dynamics derivatives
     gDq0, gDv0 = setup["ev"].node_eval_ref_jvp([], 1.0, dsl(dq), dsl(dqd), None, qdd=dsl(dqdd))
     aDq, aDv, _ = setup["ev"].rnea_derivs(dsl(dq), dsl(dqd), dsl(dqdd))
@@ -171,9 +171,13 @@ def test_fd_derivs(setup):
     dsl = lambda a: a[:, :U].contiguous()
     rA, rB, rC = setup["orc"].fd_derivs(sl(q), sl(qd), sl(tau))
     gA, gB, gC = setup["ev"].fd_derivs(dsl(dq), dsl(dqd), dsl(dtau))
-    assert rel_err(gC.cpu().numpy(), rC) < TOL
-    assert rel_err(gA.cpu().numpy(), rA) < TOL
-    assert rel_err(gB.cpu().numpy(), rB) < TOL
+    # per plane; on the 37-joint tree the planes that couple different limbs are 10^4-10^5 times smaller than the block maximum
+    # and are differences of O(max) terms through M^-1 in BOTH implementations (dual-number ABA here, complex-step ABA in the
+    # oracle), so their own-plane relative agreement is limited by conditioning: floor 1e-4 * scale there
+    fl = 1e-4 if setup["m"].n > 16 else 1e-6
+    assert rel_err_rows(gC.cpu().numpy(), rC, floor=fl) < TOL
+    assert rel_err_rows(gA.cpu().numpy(), rA, floor=fl) < TOL
+    assert rel_err_rows(gB.cpu().numpy(), rB, floor=fl) < TOL
 
 
 def test_rnea_derivs(setup):
@@ -185,9 +189,9 @@ def test_rnea_derivs(setup):
     for with_qdd in (True, False):
         rDq, rDv, rM = setup["orc"].rnea_derivs(sl(q), sl(qd), sl(qdd) if with_qdd else None)
         gDq, gDv, gM = setup["ev"].rnea_derivs(dsl(dq), dsl(dqd), dsl(dqdd) if with_qdd else None)
-        assert rel_err(gM.cpu().numpy(), rM) < TOL
-        assert rel_err(gDq.cpu().numpy(), rDq) < TOL
-        assert rel_err(gDv.cpu().numpy(), rDv) < TOL
+        assert rel_err_rows(gM.cpu().numpy(), rM) < TOL
+        assert rel_err_rows(gDq.cpu().numpy(), rDq) < TOL
+        assert rel_err_rows(gDv.cpu().numpy(), rDv) < TOL
     # M is the joint-space inertia the oracle's CRBA computes
     n = setup["m"].n
     assert rel_err(gM.cpu().numpy()[:, 0].reshape(n, n), setup["orc"].crba(q[:, 0].copy())) < TOL
@@ -211,7 +215,7 @@ def test_step_rk4_jvp(setup, direct):
     # every Jacobian entry plane relative to the scale of its own row block
     n = setup["m"].n
     for r0, r1 in ((0, n), (n, 2 * n), (2 * n, 3 * n)):
-        assert rel_err(gj[r0:r1], rj[r0:r1]) < TOL, (r0, rel_err(gj[r0:r1], rj[r0:r1]))
+        assert rel_err_rows(gj[r0:r1], rj[r0:r1]) < TOL, (r0, rel_err_rows(gj[r0:r1], rj[r0:r1]))
     # structure: d(q+,qd+)/df == 0 exactly, df+/df diagonal
     assert np.all(gj[: 2 * n, 3 * n : 4 * n] == 0.0)
     off = gj[2 * n :, 3 * n : 4 * n] * (1 - np.eye(n))[:, :, None]
@@ -240,11 +244,11 @@ def test_step_rk4_jvp_fast_motion(urdf):
     assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
     gj = gj.cpu().numpy()
     for r0, r1 in ((0, n), (n, 2 * n), (2 * n, 3 * n)):
-        assert rel_err(gj[r0:r1], rj[r0:r1]) < TOL, (r0, rel_err(gj[r0:r1], rj[r0:r1]))
+        assert rel_err_rows(gj[r0:r1], rj[r0:r1]) < TOL, (r0, rel_err_rows(gj[r0:r1], rj[r0:r1]))
     Dq, Dv, M = ev.rnea_derivs(d[0], d[1])
     rDq, rDv, rM = orc.rnea_derivs(q, qd, None)
     for got, ref in ((Dq, rDq), (Dv, rDv), (M, rM)):
-        assert rel_err(got.cpu().numpy(), ref) < TOL
+        assert rel_err_rows(got.cpu().numpy(), ref) < TOL
 
 
 # ---------------------------------------------------------------------------------------------
@@ -266,7 +270,7 @@ def test_ragged_batches_through_the_workspace_pipeline(U):
     d = [torch.from_numpy(a).cuda() for a in (q, qd, tau, f)]
     gq, gqd, gf, gj = ev.step_rk4_jvp(*d, torch.from_numpy(dtu).cuda())  # per-unit dt through K1/K3
     assert rel_err_rows(gqd.cpu().numpy(), rqd) < TOL and rel_err_rows(gf.cpu().numpy(), rf) < TOL
-    assert rel_err(gj.cpu().numpy(), rj) < TOL
+    assert rel_err_rows(gj.cpu().numpy(), rj) < TOL
 
 
 def test_workspace_smaller_than_batch_is_chunked():

@@ -200,6 +200,49 @@ def test_gpu_power_balance_at_scale():
     assert float((power - dE).abs().max()) < 1e-6 * max(1.0, float(dE.abs().max()))
 
 
+@pytest.mark.gpu
+def test_gpu_kinetic_energy_identity_at_scale():
+    """qd^T M(q) qd = sum over links of m |v_c|^2 + w^T I_c w with M from the CUDA inverse-dynamics derivative kernel
+    (mpcf_rnea_derivs_batch) and the right-hand side from the CUDA frame poses / Jacobians and the URDF text: pins the inertial
+    (M qdd) terms of the GPU path, which no reference fixture reaches (every reference call has qdd = 0), on 2^18 units."""
+    import torch
+    from mpc_fatigue_b200.evaluator import BatchEvaluator
+    from mpc_fatigue_b200.model import data_urdf
+    xml = data_urdf("pilz6")
+    m = Model.from_urdf(xml, armature=0.0)
+    ev = BatchEvaluator(m)
+    n, U = m.n, 1 << 18
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    rnd = lambda s: (torch.rand((n, U), dtype=torch.float64, device="cuda", generator=gen) * 2.0 - 1.0) * s
+    q, qd = rnd(1.5), rnd(1.0)
+    _, _, M = ev.rnea_derivs(q, qd)
+    lhs = torch.einsum("iu,iju,ju->u", qd, M.view(n, n, U), qd)
+    rhs = torch.zeros(U, dtype=torch.float64, device="cuda")
+    for link in ET.fromstring(xml).findall("link"):
+        ine = link.find("inertial")
+        if ine is None or link.get("name") not in m.frame_names:
+            continue
+        org, I = ine.find("origin"), ine.find("inertia")
+        xyz = torch.tensor([float(v) for v in ((org.get("xyz") if org is not None else None) or "0 0 0").split()], dtype=torch.float64, device="cuda")
+        rpy = [float(v) for v in ((org.get("rpy") if org is not None else None) or "0 0 0").split()]
+        Ic = np.array([[float(I.get("ixx")), float(I.get("ixy")), float(I.get("ixz"))],
+                       [float(I.get("ixy")), float(I.get("iyy")), float(I.get("iyz"))],
+                       [float(I.get("ixz")), float(I.get("iyz")), float(I.get("izz"))]])
+        Ic = torch.from_numpy(_rpy(*rpy) @ Ic @ _rpy(*rpy).T).cuda()
+        fr = m.frame_id(link.get("name"))
+        if m.export("fparent")[fr] < 0:
+            continue  # fixed to the world: no kinetic energy
+        mass = float(ine.find("mass").get("value"))
+        _, rot = ev.fk(fr, q)
+        tw = torch.einsum("rju,ju->ru", ev.jacobian(fr, q).view(6, n, U), qd)
+        R = rot.view(3, 3, U)
+        w = tw[3:]
+        vc = tw[:3] + torch.linalg.cross(w, torch.einsum("iju,j->iu", R, xyz), dim=0)
+        wl = torch.einsum("jiu,ju->iu", R, w)
+        rhs += mass * (vc * vc).sum(0) + torch.einsum("iu,ij,ju->u", wl, Ic, wl)
+    assert float((lhs - rhs).abs().max()) < 1e-10 * float(rhs.abs().max())
+
+
 # ---- joint frames keep the URDF orientation (ADVICE r1: model.cpp / urdf_model.py registered them as identity) ----
 def _rodrigues(axis, ang):
     a = np.asarray(axis, dtype=float) / np.linalg.norm(axis)
