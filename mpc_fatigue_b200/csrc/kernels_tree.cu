@@ -24,6 +24,7 @@
 //               with gamma = (1 - z + z^2/2 - z^3/4, 2 - z + z^2/2, 2 - z, 1): the RK4 response of the linear fatigue rows
 //               to a forcing applied at stage s, so the rows need no per-column recursion state.
 #include <atomic>
+#include <cstdlib>
 
 #include "launch.cuh"
 #include "tree_derivs.cuh"
@@ -33,7 +34,7 @@ namespace mpcf {
 // ------------------------------------------------------------------------------------------------ workspace layout
 struct TreeWs {
     int n, npat, NE;  // NE planes of 32 doubles per (tile, stage)
-    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n; }
+    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n + n * n; }
     MPCF_HD size_t chunk(long tile, int s) const { return ((size_t)tile * 4 + s) * NE * 32; }
     // plane indices
     MPCF_HD int dqkj(int e) const { return e; }
@@ -42,6 +43,7 @@ struct TreeWs {
     MPCF_HD int dvjk(int e) const { return 3 * npat + e; }
     MPCF_HD int lf(int e) const { return 4 * npat + e; }
     MPCF_HD int vec(int slot, int i) const { return 5 * npat + slot * n + i; }  // 0 qd_s, 1 qdd_s, 2 fnext_s, 3 q_s, 4 extra_s
+    MPCF_HD int cm(int idx) const { return 5 * npat + 5 * n + idx; }            // C = M^-1 dense, idx = row * n + col
 };
 size_t tree_ws_doubles_per_unit(int n, int npat) { return (size_t)4 * TreeWs::planes(n, npat); }
 
@@ -128,7 +130,7 @@ struct TreePackedOut {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws)
+__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws, int want_minv)
 {
     extern __shared__ double smem[];
     const int n = blob.n;
@@ -159,6 +161,12 @@ __global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, Tree
         const int e0 = m.rowptr(k), e1 = e0 + m.depth(k);  // e1 = the diagonal entry
         for (int e = e0; e < e1; ++e) o[(size_t)W.lf(e) * 32] = Mp[e];
         o[(size_t)W.lf(e1) * 32] = 1.0 / Mp[e1];
+    }
+    // C = M^-1 column by column, only for the tensor-core chain kernel (it multiplies by C instead of solving); x reuses q's storage
+    if (want_minv)
+    for (int j = 0; j < n; ++j) {
+        TreeDerivs<GenericModel<MAXN>>::minv_column(m, Mp, j, q);
+        for (int i = 0; i < n; ++i) o[(size_t)W.cm(i * n + j) * 32] = q[i];
     }
 }
 
@@ -409,11 +417,243 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
     cp_async_wait<0>();
 }
 
+
+// ------------------------------------------------------------------------------------------------ T3 on the FP64 tensor cores
+// Same recursion as k_tree_chain with both per-stage products as DMMA (mma.sync m8n8k4 f64) GEMMs, n <= 37 (<= 112 columns):
+//   Z = [dID/dq | dID/dqd] . [X[q] ; X[qd]]      M = 40, K = 2n (<= 76), N = 112: 5 m-tiles x 14 n-tiles x 19 k-steps
+//   K = C . (E_tau - Z),  C = M^-1 from k_tree_derivs   M = 40, K = 40: the B operand comes straight from Z's accumulator
+//                                                     fragments through warp shuffles (no shared-memory round trip)
+// A warp owns the n-tiles w, w + 4, w + 8, w + 12, i.e. its own 32 Jacobian columns of X (so X needs only __syncwarp), keeps
+// 5 x 4 accumulator fragments per product in registers, and reads operands with conflict-free 8-byte loads (row strides 76 /
+// 44 / 116 doubles = 12, 12, 4 mod 16).  Per k-step: 5 + 4 loads feed 20 DMMA (5120 FMA): the arithmetic, not shared-memory
+// bandwidth, is the bound here (the scalar kernel needs one 16-byte broadcast load per two DFMA and is bound by that).
+MPCF_DI void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NR>
+__global__ void __launch_bounds__(128, 2) k_tree_chain_mma(TreeChainArgs a)
+{
+    constexpr int MT = NR / 8;        // m-tiles
+    constexpr int RSA = 2 * NR - 4;   // row stride of DA = [dID/dq | dID/dqd] (76: conflict-free, K <= 76)
+    constexpr int RSC = NR + 4;       // row stride of C (44)
+    constexpr int XS = 116;           // row stride of X = [X[q] ; X[qd]] (k-major), up to 112 columns
+    const TreeWs W = a.W;
+    const int n = W.n, npat = W.npat;
+    const int NC = 3 * n + 1, NT = (NC + 7) / 8;
+    const int K1 = (2 * n + 3) & ~3;  // k extent of the first product
+    extern __shared__ __align__(16) double sm[];
+    double *DA = sm, *Cm = DA + NR * RSA, *V = Cm + NR * RSC, *Xs = V + 2 * 4 * NR;
+    unsigned short *okj = reinterpret_cast<unsigned short *>(Xs + RSA * XS), *ojk = okj + npat;
+    const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
+    for (int i = t; i < NR * RSA + NR * RSC + 2 * 4 * NR; i += 128) sm[i] = 0.0;
+    {
+        const int *parent = a.ints, *depth = a.ints + 3 * n, *rowptr = a.ints + 4 * n;
+        for (int k = t; k < n; k += 128)
+            for (int j = k; j >= 0; j = parent[j]) {
+                const int e = rowptr[k] + depth[j];
+                okj[e] = (unsigned short)(k * RSA + j);  // entry (row k, col j), row-major
+                ojk[e] = (unsigned short)(j * RSA + k);
+            }
+    }
+    __syncthreads();
+    const unsigned sDA = (unsigned)__cvta_generic_to_shared(DA), sCm = (unsigned)__cvta_generic_to_shared(Cm), sV = (unsigned)__cvta_generic_to_shared(V);
+    auto issue_A = [&](long u, int s) {
+        const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
+        for (int e = t; e < npat; e += 128) {
+            const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
+            cp_async8s(sDA + kj, ws + (size_t)W.dqkj(e) * 32);
+            cp_async8s(sDA + kj + (unsigned)n * 8u, ws + (size_t)W.dvkj(e) * 32);
+            if (kj != jk) {
+                cp_async8s(sDA + jk, ws + (size_t)W.dqjk(e) * 32);
+                cp_async8s(sDA + jk + (unsigned)n * 8u, ws + (size_t)W.dvjk(e) * 32);
+            }
+        }
+        const unsigned vb = sV + (unsigned)((s & 1) * 4 * NR) * 8u;
+        for (int i = t; i < n; i += 128) {
+            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, ws + (size_t)W.vec(0, i) * 32);
+            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, ws + (size_t)W.vec(1, i) * 32);
+            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, ws + (size_t)W.vec(2, i) * 32);
+            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, ws + (size_t)W.vec(4, i) * 32);
+        }
+        cp_async_commit();
+    };
+    auto issue_B = [&](long u, int s) {
+        const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
+        for (int idx = t; idx < n * n; idx += 128) {
+            const int i = idx / n, j = idx - i * n;
+            cp_async8s(sCm + (unsigned)(i * RSC + j) * 8u, ws + (size_t)W.cm(idx) * 32);
+        }
+        cp_async_commit();
+    };
+    // scratch: [2][MT * 4 * 2 fragment slots][128 threads], coalesced
+    double *AF = a.scratch + (size_t)blockIdx.x * 2 * NR * 128 + t, *Ps = AF + (size_t)NR * 128;
+    const long PC = 4 * n + 1;
+    long u = blockIdx.x;
+    if (u < a.cnt) { issue_A(u, 0); issue_B(u, 0); }
+    for (; u < a.cnt; u += gridDim.x) {
+        const double h = a.dt_u ? a.dt_u[u] : a.dt;
+        // X1 = identity on the (q, qd) columns: every warp initialises its own 32 columns (lane -> column 8 nt_{l/8} + l % 8)
+        {
+            const int ntc = w + 4 * (l >> 3), c = 8 * ntc + (l & 7);
+            if (ntc < NT)
+                for (int k = 0; k < K1; ++k) Xs[k * XS + c] = (k == c && k < 2 * n) ? 1.0 : 0.0;
+        }
+        __syncwarp();
+        double acc[MT][4][2], yv[MT][4][2];
+#pragma unroll 1
+        for (int s = 0; s < 4; ++s) {
+            const long un = u + gridDim.x;
+            const bool more = s < 3 || un < a.cnt;
+            const long u2 = s < 3 ? u : un;
+            const int s2 = s < 3 ? s + 1 : 0;
+            cp_async_wait<1>();
+            __syncthreads();
+            // ---- product 1 ----
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+#pragma unroll 1
+            for (int ks = 0; ks < K1 / 4; ++ks) {
+                double af[MT], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) af[mt] = DA[(8 * mt + g) * RSA + 4 * ks + tq];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = (w + 4 * j < NT) ? Xs[(4 * ks + tq) * XS + 8 * (w + 4 * j) + g] : 0.0;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af[mt], bf[j]);
+            }
+            __syncthreads();
+            if (more) issue_A(u2, s2); else cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            // ---- rhs = E_tau - Z (element (r, c): r = 8 mt + g, c = 8 (w + 4 j) + 2 tq + e) ----
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
+                        acc[mt][j][e] = ((r < n && c == 2 * n + r) ? 1.0 : 0.0) - acc[mt][j][e];
+                    }
+            // ---- product 2: K = C rhs; B fragment (k = 4 ks + tq, col g) from lane 4 ((4 ks + tq) % 8) + g / 2, element g % 2 ----
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < NR / 4; ++ks) {
+                double af[MT], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) af[mt] = Cm[(8 * mt + g) * RSC + 4 * ks + tq];
+                const int src = 4 * (4 * (ks & 1) + tq) + (g >> 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double v0 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][0], src), v1 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][1], src);
+                    bf[j] = (g & 1) ? v1 : v0;
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(yv[mt][j][0], yv[mt][j][1], af[mt], bf[j]);
+            }
+            __syncthreads();
+            if (more) issue_B(u2, s2); else cp_async_commit();
+            // ---- update ----
+            const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+            const double *Vs = V + (s & 1) * 4 * NR;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
+                        const int slot = ((mt * 4 + j) * 2 + e) * 128;
+                        if (r < n && c < NC) {
+                            const bool isdt = c == 3 * n;
+                            const double y = h * yv[mt][j][e] + (isdt ? Vs[1 * NR + r] : 0.0);
+                            yv[mt][j][e] = y;
+                            const double x1q = (c == r) ? 1.0 : 0.0, x1v = (c == n + r) ? 1.0 : 0.0;
+                            double *jcol = a.jac + (size_t)(isdt ? 4 * n : c) * a.UJ + u;
+                            if (s == 0) {
+                                jcol[(size_t)(n + r) * PC * a.UJ] = x1v - y * (1.0 / 6.0);
+                                Ps[slot] = y;
+                                AF[slot] = Vs[2 * NR + r] * y + (isdt ? Vs[3 * NR + r] : 0.0);
+                            } else if (s < 3) {
+                                atomicAdd(Ps + slot, y);
+                                atomicAdd(AF + slot, Vs[2 * NR + r] * y + ((s == 1 && c == n + r) ? Vs[3 * NR + r] : 0.0));
+                            }
+                            const double xvold = Xs[(n + r) * XS + c];
+                            const double yq = h * xvold + (isdt ? Vs[0 * NR + r] : 0.0);
+                            Xs[r * XS + c] = x1q + cs * yq;
+                            Xs[(n + r) * XS + c] = x1v + cs * y;
+                        }
+                    }
+            if (s == 3) {
+                // ---- epilogue: per m-tile, the scratch loads first (one round trip), then the stores ----
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    double Pv[4][2], Av[4][2];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
+                            const int slot = ((mt * 4 + j) * 2 + e) * 128;
+                            if (r < n && c < NC) { Pv[j][e] = Ps[slot]; Av[j][e] = AF[slot]; }
+                        }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
+                            if (r < n && c < NC) {
+                                const bool isdt = c == 3 * n;
+                                const double x1q = (c == r) ? 1.0 : 0.0, x1v = (c == n + r) ? 1.0 : 0.0;
+                                double *jcol = a.jac + (size_t)(isdt ? 4 * n : c) * a.UJ + u;
+                                jcol[(size_t)r * PC * a.UJ] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pv[j][e] + (isdt ? Vs[3 * NR + r] : 0.0);
+                                atomicAdd(jcol + (size_t)(n + r) * PC * a.UJ, (2.0 * Pv[j][e] + yv[mt][j][e]) * (1.0 / 6.0));
+                                double afv = Av[j][e];
+                                if (c == 2 * n + r) {
+                                    const double z = a.fat[4 * r] * h;
+                                    afv += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                                }
+                                jcol[(size_t)(2 * n + r) * PC * a.UJ] = afv;
+                            }
+                        }
+                }
+            }
+            __syncwarp();
+        }
+        for (int idx = t; idx < 3 * n * n; idx += 128) {
+            const int r = idx / n, j = idx - r * n;
+            double v = 0.0;
+            if (r == 2 * n + j) {
+                const double z = a.fat[4 * j] * h;
+                v = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
+            }
+            a.jac[((size_t)r * PC + 3 * n + j) * a.UJ + u] = v;
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------------------------------------ launcher
 static std::atomic<bool> g_tree_attr[64];
 
 bool tree_jvp_supported(const LaunchModel &m) { return (m.fam == FAM_GENERIC16 || m.fam == FAM_GENERIC64) && m.n <= 40; }
 
+static size_t tree_chain_mma_smem(int NR, int npat)
+{
+    const int RSA = 2 * NR - 4, RSC = NR + 4, XS = 116;
+    return ((size_t)NR * RSA + (size_t)NR * RSC + 2 * 4 * NR + (size_t)RSA * XS) * sizeof(double) + (size_t)2 * npat * sizeof(unsigned short);
+}
 static size_t tree_chain_smem(int n, int NR, int npat)
 {
     const int NC = 3 * n + 1, XS = (NC + 15) & ~15;
@@ -437,12 +677,14 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tree_chain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tree_chain_mma<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024);
+        if (e != cudaSuccess) return e;
         g_tree_attr[dev].store(true, std::memory_order_release);
     }
     const int ctas_per_sm = smem3 <= 113 * 1024 ? 2 : 1;
     const long grid3_max = (long)nsm * ctas_per_sm;
     // workspace = [stage data of the chunk][fatigue-row scratch of the chain kernel's CTAs]
-    const size_t scratch_bytes = (size_t)grid3_max * 2 * n * 128 * sizeof(double);
+    const size_t scratch_bytes = (size_t)grid3_max * 2 * 40 * 128 * sizeof(double);
     if (ws_bytes <= scratch_bytes) return cudaErrorInvalidValue;
     const size_t per_unit = tree_ws_doubles_per_unit(n, npat) * sizeof(double);
     long Uc = (long)((ws_bytes - scratch_bytes) / per_unit);
@@ -455,10 +697,18 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         const unsigned gb = (unsigned)((c + kThreads - 1) / kThreads);
         k_tree_stages<MAXN><<<gb, kThreads, smem12, s>>>(m.blob, W, U, c, q + u0, qd + u0, tau + u0, f + u0, dt, dt_u ? dt_u + u0 : nullptr,
                                                         qn ? qn + u0 : nullptr, qdn ? qdn + u0 : nullptr, fn ? fn + u0 : nullptr, ws);
-        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws);
+        // MPCF_TREE_MMA=1 selects the FP64 tensor-core chain kernel (n in 17..37).  Measured on the 37-joint tree: 18.6 ms per 33k
+        // units against 19.5 ms for the scalar kernel, but it needs M^-1 from k_tree_derivs, which costs 13 ms more than the
+        // factor alone (latency-bound sparse solves in local memory), so the scalar kernel is the default (profiles/r02_c4.md).
+        const char *env = getenv("MPCF_TREE_MMA");
+        const bool use_mma = env && atoi(env) != 0 && NR == 40 && n > 16 && n <= 37 && tree_chain_mma_smem(40, npat) <= 113 * 1024;
+        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_mma ? 1 : 0);
         TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
         const unsigned g3 = (unsigned)(c < grid3_max ? c : grid3_max);
-        k_tree_chain<NR><<<g3, 128, smem3, s>>>(a);
+        if (use_mma)
+            k_tree_chain_mma<40><<<g3, 128, tree_chain_mma_smem(40, npat), s>>>(a);
+        else
+            k_tree_chain<NR><<<g3, 128, smem3, s>>>(a);
         g_launches.fetch_add(3);
     }
     return cudaGetLastError();
@@ -468,7 +718,7 @@ size_t tree_jvp_workspace_bytes(int n, int npat, long U)
 {
     long units = U < (1L << 15) ? U : (1L << 15);  // chunks of at most 32768 units (1.9 GB for the 37-joint tree)
     units = (units + 31) / 32 * 32;
-    const size_t scratch = (size_t)148 * 4 * 2 * n * 128 * sizeof(double);  // generous: up to 2x the CTAs of a 148-SM part
+    const size_t scratch = (size_t)148 * 4 * 2 * 40 * 128 * sizeof(double);  // generous: up to 2x the CTAs of a 148-SM part
     return (size_t)units * tree_ws_doubles_per_unit(n, npat) * sizeof(double) + scratch;
 }
 

@@ -152,6 +152,26 @@ struct TreeDerivs {
         }
         return ok;
     }
+    // column j of C = M^-1 from the packed factor (entry (k, a): L_ka, entry (k, k): D_k; M = L^T D L): L^T y = e_j touches only
+    // the ancestors of j, then w = D^-1 y, then L x = w row by row along the ancestor chains.  x: caller scratch [n].
+    static MPCF_HD void minv_column(const MP &m, const double *Mp, int j, double *x)
+    {
+        const int n = m.n();
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+        x[j] = 1.0;
+        for (int k = j; k >= 0; k = m.parent(k)) {
+            const double yk = x[k];
+            const int rk = m.rowptr(k);
+            for (int i = m.parent(k); i >= 0; i = m.parent(i)) x[i] -= Mp[rk + m.depth(i)] * yk;
+        }
+        for (int k = j; k >= 0; k = m.parent(k)) x[k] /= Mp[m.rowptr(k) + m.depth(k)];
+        for (int i = 0; i < n; ++i) {
+            double s = x[i];
+            const int ri = m.rowptr(i);
+            for (int a = m.parent(i); a >= 0; a = m.parent(a)) s -= Mp[ri + m.depth(a)] * x[a];
+            x[i] = s;
+        }
+    }
     static MPCF_HD double nan_value_hd()
     {
         const double zero = 0.0;

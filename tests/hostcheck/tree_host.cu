@@ -54,7 +54,7 @@ struct Topo {
 // Dq, Dv, M dense [n][n]; Lfac dense [n][n] (strictly lower: L_kj; diagonal: D_k) from the packed in-place factorisation
 extern "C" int hc_tree_derivs(int n, const int *parent, const int *jtype, const double *Rp, const double *pp, const double *mass, const double *mc,
                               const double *Io, const double *arm, const double *grav, const double *q, const double *qd, const double *qdd,
-                              double *Dq, double *Dv, double *M, double *Lfac)
+                              double *Dq, double *Dv, double *M, double *Lfac, double *Cinv)
 {
     Topo tp(n, parent);
     HostTree m{n, parent, jtype, tp.depth.data(), tp.rowptr.data(), Rp, pp, mass, mc, Io, arm, grav};
@@ -73,6 +73,13 @@ extern "C" int hc_tree_derivs(int n, const int *parent, const int *jtype, const 
     const bool ok = TreeDerivs<HostTree>::factorize(m, Mp.data());
     for (int k = 0; k < n; ++k)
         for (int j = k; j >= 0; j = parent[j]) Lfac[k * n + j] = Mp[tp.rowptr[k] + tp.depth[j]];
+    if (Cinv) {
+        std::vector<double> x(n);
+        for (int j = 0; j < n; ++j) {
+            TreeDerivs<HostTree>::minv_column(m, Mp.data(), j, x.data());
+            for (int i = 0; i < n; ++i) Cinv[i * n + j] = x[i];
+        }
+    }
     return ok ? 0 : -1;
 }
 

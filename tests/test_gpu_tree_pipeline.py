@@ -103,3 +103,12 @@ def test_c4_sample_of_the_full_size_batch():
     rq, rqd, rf, rj = orc.step_rk4_jvp(*[t.cpu().numpy() for t in (q, qd, tau, f)], 0.5 / 40)
     assert rel_err_rows(gq, rq) < TOL and rel_err_rows(gqd, rqd) < TOL and rel_err_rows(gf, rf) < TOL
     assert rel_err_rows(gj.reshape(-1, U), rj.reshape(-1, U)) < TOL
+
+
+def test_tensor_core_chain_kernel_matches_the_oracle(monkeypatch):
+    """MPCF_TREE_MMA=1: the same recursion with both per-stage products on the FP64 tensor cores (mma.sync m8n8k4, the second
+    product's B operand shuffled out of the first one's accumulator fragments) and M^-1 from k_tree_derivs."""
+    monkeypatch.setenv("MPCF_TREE_MMA", "1")
+    _check(MODELS["humanoid37"](), 130, 0.0125, seed=46)
+    dt_u = np.ascontiguousarray(np.random.default_rng(2).uniform(0.002, 0.02, 33))
+    _check(MODELS["humanoid37"](), 33, 0.0, seed=47, dt_u=dt_u)

@@ -40,7 +40,7 @@ def _model_args(m):
 
 def _derivs(lib, m, margs, q, qd, qdd):
     n = m.n
-    out = [np.zeros((n, n)) for _ in range(4)]
+    out = [np.zeros((n, n)) for _ in range(5)]
     rc = lib.hc_tree_derivs(*margs, _p(np.ascontiguousarray(q)), _p(np.ascontiguousarray(qd)), _p(np.ascontiguousarray(qdd)), *[_p(o) for o in out])
     assert rc == 0
     return out
@@ -64,7 +64,8 @@ def test_tree_id_derivatives_and_factorisation(lib, name):
     keep, margs = _model_args(m)
     par = keep["parent"]
     for u in range(U):
-        Dq, Dv, M, Lf = _derivs(lib, m, margs, q[:, u], qd[:, u], qdd[:, u])
+        Dq, Dv, M, Lf, Ci = _derivs(lib, m, margs, q[:, u], qd[:, u], qdd[:, u])
+        assert np.abs(Ci @ M - np.eye(n)).max() < 1e-9  # M^-1 column by column from the packed factor
         for got, ref, nm in ((Dq, rDq, "dID/dq"), (Dv, rDv, "dID/dqd"), (M, rM, "M")):
             ref = ref[:, u].reshape(n, n)
             assert np.abs(got - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (name, nm, u)
