@@ -74,7 +74,7 @@ def work_model() -> dict:
         return {}
 
 
-def roofline_for(family: str, n: int, units: float, kernel_ms: dict, peak_tflops: float, hbm_peak: float, peak_src: str) -> dict:
+def roofline_for(family: str, n: int, units: float, kernel_ms: dict, peak_tflops: float, hbm_peak: float, peak_src: str, total_ms: float | None = None) -> dict:
     """FP64 roofline of one config.  achieved = ALGORITHMIC FLOP per unit x units / device time of the pipeline kernels,
     with FLOP per unit = min(frozen dual-number model, instrumented count of the shipped algorithm) ("whichever
     is smaller"); `fp64_pipe` = executed FP64 instructions (every DADD/DMUL/DFMA occupies one issue slot of the pipe whose
@@ -82,7 +82,7 @@ def roofline_for(family: str, n: int, units: float, kernel_ms: dict, peak_tflops
     recomputed from this run's own kernel times."""
     fm = frozen_flop_model(n)
     wm = work_model().get(family)
-    total_ms = sum(kernel_ms.values())
+    total_ms = total_ms if total_ms is not None else sum(kernel_ms.values())  # device time of the whole Jacobian call (events around it)
     out = {"bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops, "peak_source": peak_src, "kernel_ms": total_ms, "kernels_ms": kernel_ms}
     flop_frozen = fm["step_jac"]
     if wm:
@@ -474,7 +474,7 @@ def pcie_probe(dev) -> dict:
 def config_result(name: str, runner: ConfigRunner, t: dict, steps: int, world: int, peak_tf: float, hbm_peak: float, peak_src: str) -> dict:
     units_per_step = world * runner.U
     value = units_per_step * steps / (t["el_ms"] * 1e-3)
-    roof = roofline_for(runner.family, runner.n, runner.U, t["kern"], peak_tf, hbm_peak, peak_src)
+    roof = roofline_for(runner.family, runner.n, runner.U, t["kern"], peak_tf, hbm_peak, peak_src, total_ms=t["jvp_ms"])
     return {"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": t["el_ms"] / steps, "steps": steps,
             "scaling": CONFIGS[name]["scaling"], "config": workload_config(name, world), "chunks_per_step": runner.nchunks,
             "scenarios_per_chunk": runner.Bc, "kernel_family": runner.family, "gpu_launches": t["launches"], "roofline": roof,

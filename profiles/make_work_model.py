@@ -12,10 +12,13 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 # family -> (raw csv, units per launch, {label: kernel-name regex}, multiplier per label)
 SOURCES = {
-    "chain6": ("r01_jvp_pipeline_v6_raw.csv", 1048576, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule"}, 1),
-    "forest12x6": ("r02/r02_c3_jvp_raw.csv", 409600, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule"}, 1),
-    # run-time tree: one launch = 2560 units x 112 seed directions (blockIdx.y); the counters are per launch
-    "generic64": ("r02/r02_c4_jvp_raw.csv", 2560, {"step_rk4_jvp": "generic_kernel"}, 1),
+    # python profiles/run_kernel.py jvp 16384 2, launches 7-9: one full chunk of 2^20 units
+    "chain6": ("r02/r02_c2_jvp_raw.csv", 1048576, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule"}, 1),
+    # python profiles/run_kernel.py jvp 4096 1 pilz6x2c 100, launches 9-16: coupled-fatigue pre kernel, both chains, post kernel
+    "forest12x6": ("r02/r02_c3_jvp_raw.csv", 409600, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule",
+                                                     "couple": "k_couple"}, 1),
+    # python profiles/run_kernel.py jvp 1024 1 humanoid37 40, launches 7-9: the tree pipeline on its first chunk (33,008 units)
+    "generic64": ("r02/r02_c4_tree_raw.csv", 33008, {"tree_stages": "k_tree_stages", "tree_derivs": "k_tree_derivs", "tree_chain": "k_tree_chain"}, 1),
 }
 
 
@@ -50,10 +53,7 @@ def main():
                 rows[1][ix["dram__bytes_read.sum"]], 1) / units
         # a capture that holds the same kernel several times for the SAME units (repeated passes) is averaged; the two chains of
         # a forest are different work on the same units and are summed
-        reps = 1 if fam != "forest12x6" else 1
-        if fam == "forest12x6":
-            # the capture holds two passes x two chains: launches = 4 per label -> per unit = sum / 2 passes
-            reps = max(1, min(k["launches"] for k in kernels.values()) // 2)
+        reps = 1  # every capture holds exactly one pass over its units (the two chains of a forest are summed)
         for k in kernels.values():
             for op in ("dadd", "dmul", "dfma"):
                 k[op] = round(k[op] / reps * mult)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Profiling driver: launches one hot-path kernel a few times on the C2 workload shape (smaller B by default).
-    python profiles/run_kernel.py jvp|step|rnea|node [B] [reps] [pilz6|pilz6x2|humanoid37] [N]
+    python profiles/run_kernel.py jvp|step|rnea|node [B] [reps] [pilz6|pilz6x2|pilz6x2c|humanoid37] [N]
 Used under ncu (see profiles/README.md); never a source of bench numbers."""
 import os
 import sys
@@ -19,7 +19,14 @@ mname = sys.argv[4] if len(sys.argv) > 4 else "pilz6"
 N = int(sys.argv[5]) if len(sys.argv) > 5 else 100
 dt = 0.02
 dev = torch.device("cuda", 0)
-m = Model.synthetic("humanoid", 37, seed=7, armature=1e-2) if mname == "humanoid37" else Model.from_urdf(data_urdf(mname), armature=1e-2)
+if mname == "humanoid37":
+    m = Model.synthetic("humanoid", 37, seed=7, armature=1e-2)
+elif mname == "pilz6x2c":  # config C3: both arms with the coupled fatigue (box load split)
+    from mpc_fatigue_b200.coupling import box_load_coupling
+    m = Model.from_urdf(data_urdf("pilz6x2"), armature=1e-2)
+    m.set_coupling(box_load_coupling(m))
+else:
+    m = Model.from_urdf(data_urdf(mname), armature=1e-2)
 ev = BatchEvaluator(m, dev)
 lim = {k: m.export(k) for k in ("q_lo", "q_hi", "v_max", "tau_max")}
 q, qd, tau, f = synth_batch(lim, 0, B, N, device=dev)
