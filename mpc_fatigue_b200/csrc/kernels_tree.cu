@@ -34,7 +34,7 @@ namespace mpcf {
 // ------------------------------------------------------------------------------------------------ workspace layout
 struct TreeWs {
     int n, npat, NE;  // NE planes of 32 doubles per (tile, stage)
-    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n + n * n; }
+    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n; }
     MPCF_HD size_t chunk(long tile, int s) const { return ((size_t)tile * 4 + s) * NE * 32; }
     // plane indices
     MPCF_HD int dqkj(int e) const { return e; }
@@ -43,7 +43,6 @@ struct TreeWs {
     MPCF_HD int dvjk(int e) const { return 3 * npat + e; }
     MPCF_HD int lf(int e) const { return 4 * npat + e; }
     MPCF_HD int vec(int slot, int i) const { return 5 * npat + slot * n + i; }  // 0 qd_s, 1 qdd_s, 2 fnext_s, 3 q_s, 4 extra_s
-    MPCF_HD int cm(int idx) const { return 5 * npat + 5 * n + idx; }            // C = M^-1 dense, idx = row * n + col
 };
 size_t tree_ws_doubles_per_unit(int n, int npat) { return (size_t)4 * TreeWs::planes(n, npat); }
 
@@ -130,7 +129,7 @@ struct TreePackedOut {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws, int want_minv)
+__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws, int want_linv)
 {
     extern __shared__ double smem[];
     const int n = blob.n;
@@ -157,16 +156,12 @@ __global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, Tree
     TreeDerivs<GenericModel<MAXN>>::forward(m, q, qd, qdd, rec);
     TreeDerivs<GenericModel<MAXN>>::backward(m, rec, comp, Mp, out);
     TreeDerivs<GenericModel<MAXN>>::factorize(m, Mp);
+    // the tensor-core chain kernel multiplies by L^-1 (same packed pattern) instead of solving with L; path / lrow reuse q / qd
+    if (want_linv) TreeDerivs<GenericModel<MAXN>>::invert_unit_factor(m, Mp, reinterpret_cast<int *>(q), qd);
     for (int k = 0; k < n; ++k) {
         const int e0 = m.rowptr(k), e1 = e0 + m.depth(k);  // e1 = the diagonal entry
         for (int e = e0; e < e1; ++e) o[(size_t)W.lf(e) * 32] = Mp[e];
         o[(size_t)W.lf(e1) * 32] = 1.0 / Mp[e1];
-    }
-    // C = M^-1 column by column, only for the tensor-core chain kernel (it multiplies by C instead of solving); x reuses q's storage
-    if (want_minv)
-    for (int j = 0; j < n; ++j) {
-        TreeDerivs<GenericModel<MAXN>>::minv_column(m, Mp, j, q);
-        for (int i = 0; i < n; ++i) o[(size_t)W.cm(i * n + j) * 32] = q[i];
     }
 }
 
@@ -419,55 +414,68 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
 
 
 // ------------------------------------------------------------------------------------------------ T3 on the FP64 tensor cores
-// Same recursion as k_tree_chain with both per-stage products as DMMA (mma.sync m8n8k4 f64) GEMMs, n <= 37 (<= 112 columns):
-//   Z = [dID/dq | dID/dqd] . [X[q] ; X[qd]]      M = 40, K = 2n (<= 76), N = 112: 5 m-tiles x 14 n-tiles x 19 k-steps
-//   K = C . (E_tau - Z),  C = M^-1 from k_tree_derivs   M = 40, K = 40: the B operand comes straight from Z's accumulator
-//                                                     fragments through warp shuffles (no shared-memory round trip)
-// A warp owns the n-tiles w, w + 4, w + 8, w + 12, i.e. its own 32 Jacobian columns of X (so X needs only __syncwarp), keeps
-// 5 x 4 accumulator fragments per product in registers, and reads operands with conflict-free 8-byte loads (row strides 76 /
-// 44 / 116 doubles = 12, 12, 4 mod 16).  Per k-step: 5 + 4 loads feed 20 DMMA (5120 FMA): the arithmetic, not shared-memory
-// bandwidth, is the bound here (the scalar kernel needs one 16-byte broadcast load per two DFMA and is bound by that).
+// Same recursion with every per-stage product as DMMA (mma.sync m8n8k4 f64) GEMMs.  CTA = (unit, slab of 64 Jacobian
+// columns), 4 warps x 16 columns, two CTAs per SM; all column state of a warp is warp-private, so the only block-wide
+// barriers are the ones that swap the stage matrices:
+//   Z = [dID/dq | dID/dqd] . [X[q] ; X[qd]]     M = NR, K = 2 NR, N = 64   (stage 1: Z is a column of the matrices, no product)
+//   T = D^-1 L^-T (E_tau - Z),  K = L^-1 T      with L^-1 from k_tree_derivs (invert_unit_factor: same ancestor pattern as L), so
+//                                               M^-1 = L^-1 D^-1 L^-T is two TRIANGULAR products (only the tiles on or below /
+//                                               above the diagonal are issued); the B operands come straight from the previous
+//                                               product's accumulator fragments through warp shuffles
+// Accumulators P and the fatigue-row sums are register fragments (2 n-tiles x MT m-tiles per warp = 4 MT doubles each per
+// thread), X lives in shared memory k-major (row stride 68 = 4 mod 16: conflict-free B-fragment loads), the matrices row-major
+// with strides 2 NR + 4 / NR + 4 (conflict-free A-fragment loads, both of L^-1 and of its transpose).
 MPCF_DI void dmma884(double &c0, double &c1, double a, double b)
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+MPCF_DI void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
 template <int NR>
-__global__ void __launch_bounds__(128, 2) k_tree_chain_mma(TreeChainArgs a)
+struct TcLayout {
+    static constexpr int MT = NR / 8, RSA = 2 * NR + 4, RSL = NR + 4, XS = 68, KS1 = NR / 2, KS2 = NR / 4;
+    static constexpr int oDA = 0, oLI = oDA + NR * RSA, oDI = oLI + NR * RSL, oV = oDI + NR, oX = oV + 2 * 4 * NR, nD = oX + 2 * NR * XS;
+    static size_t bytes(int npat) { return (size_t)nD * sizeof(double) + (size_t)3 * npat * sizeof(unsigned short); }
+};
+
+template <int NR>
+__global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
 {
-    constexpr int MT = NR / 8;        // m-tiles
-    constexpr int RSA = 2 * NR - 4;   // row stride of DA = [dID/dq | dID/dqd] (76: conflict-free, K <= 76)
-    constexpr int RSC = NR + 4;       // row stride of C (44)
-    constexpr int XS = 116;           // row stride of X = [X[q] ; X[qd]] (k-major), up to 112 columns
+    using Ly = TcLayout<NR>;
+    constexpr int MT = Ly::MT, RSA = Ly::RSA, RSL = Ly::RSL, XS = Ly::XS, KS1 = Ly::KS1, KS2 = Ly::KS2;
     const TreeWs W = a.W;
     const int n = W.n, npat = W.npat;
-    const int NC = 3 * n + 1, NT = (NC + 7) / 8;
-    const int K1 = (2 * n + 3) & ~3;  // k extent of the first product
+    const int NC = 3 * n + 1;
     extern __shared__ __align__(16) double sm[];
-    double *DA = sm, *Cm = DA + NR * RSA, *V = Cm + NR * RSC, *Xs = V + 2 * 4 * NR;
-    unsigned short *okj = reinterpret_cast<unsigned short *>(Xs + RSA * XS), *ojk = okj + npat;
+    double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *Xs = sm + Ly::oX;
+    unsigned short *okj = reinterpret_cast<unsigned short *>(sm + Ly::nD), *ojk = okj + npat, *okl = ojk + npat;
     const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
-    for (int i = t; i < NR * RSA + NR * RSC + 2 * 4 * NR; i += 128) sm[i] = 0.0;
+    const int slab = blockIdx.y, nslab = gridDim.y;
+    for (int i = t; i < Ly::oX; i += 128) sm[i] = 0.0;
+    __syncthreads();
     {
         const int *parent = a.ints, *depth = a.ints + 3 * n, *rowptr = a.ints + 4 * n;
-        for (int k = t; k < n; k += 128)
+        for (int k = t; k < n; k += 128) {
+            LI[k * RSL + k] = 1.0;  // unit diagonal of L^-1 (the padding rows stay 0, so the padding rows of every product are 0)
             for (int j = k; j >= 0; j = parent[j]) {
                 const int e = rowptr[k] + depth[j];
-                okj[e] = (unsigned short)(k * RSA + j);  // entry (row k, col j), row-major
+                okj[e] = (unsigned short)(k * RSA + j);  // entry (row k, col j) of [dID/dq | dID/dqd], row-major
                 ojk[e] = (unsigned short)(j * RSA + k);
+                okl[e] = (unsigned short)(j == k ? NR * RSL + k : k * RSL + j);  // L^-1_kj, or 1 / D_k into the vector behind the matrix
             }
+        }
     }
     __syncthreads();
-    const unsigned sDA = (unsigned)__cvta_generic_to_shared(DA), sCm = (unsigned)__cvta_generic_to_shared(Cm), sV = (unsigned)__cvta_generic_to_shared(V);
+    const unsigned sDA = (unsigned)__cvta_generic_to_shared(DA), sLI = (unsigned)__cvta_generic_to_shared(LI), sV = (unsigned)__cvta_generic_to_shared(V);
     auto issue_A = [&](long u, int s) {
         const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
         for (int e = t; e < npat; e += 128) {
             const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
             cp_async8s(sDA + kj, ws + (size_t)W.dqkj(e) * 32);
-            cp_async8s(sDA + kj + (unsigned)n * 8u, ws + (size_t)W.dvkj(e) * 32);
+            cp_async8s(sDA + kj + (unsigned)NR * 8u, ws + (size_t)W.dvkj(e) * 32);
             if (kj != jk) {
                 cp_async8s(sDA + jk, ws + (size_t)W.dqjk(e) * 32);
-                cp_async8s(sDA + jk + (unsigned)n * 8u, ws + (size_t)W.dvjk(e) * 32);
+                cp_async8s(sDA + jk + (unsigned)NR * 8u, ws + (size_t)W.dvjk(e) * 32);
             }
         }
         const unsigned vb = sV + (unsigned)((s & 1) * 4 * NR) * 8u;
@@ -481,27 +489,33 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_mma(TreeChainArgs a)
     };
     auto issue_B = [&](long u, int s) {
         const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
-        for (int idx = t; idx < n * n; idx += 128) {
-            const int i = idx / n, j = idx - i * n;
-            cp_async8s(sCm + (unsigned)(i * RSC + j) * 8u, ws + (size_t)W.cm(idx) * 32);
-        }
+        for (int e = t; e < npat; e += 128) cp_async8s(sLI + okl[e] * 8u, ws + (size_t)W.lf(e) * 32);
         cp_async_commit();
     };
-    // scratch: [2][MT * 4 * 2 fragment slots][128 threads], coalesced
-    double *AF = a.scratch + (size_t)blockIdx.x * 2 * NR * 128 + t, *Ps = AF + (size_t)NR * 128;
+    // this thread's fragment elements: rows 8 mt + g, columns cb + 8 j + 2 tq + e (cb = the warp's first column)
+    const int cb = 64 * slab + 16 * w;
     const long PC = 4 * n + 1;
+    unsigned mq = 0, mv = 0, mt_ = 0;  // bit (mt * 2 + j) * 2 + e: X1[q] = 1, X1[qd] = 1, tau-column unit entry
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 8 * mt + g, c = cb + 8 * j + 2 * tq + e, bit = (mt * 2 + j) * 2 + e;
+                if (r < n && c == r) mq |= 1u << bit;
+                if (r < n && c == n + r) mv |= 1u << bit;
+                if (r < n && c == 2 * n + r) mt_ |= 1u << bit;
+            }
+    const bool dt0 = cb + 2 * tq == 3 * n, dt1 = cb + 2 * tq + 1 == 3 * n, dt2 = cb + 8 + 2 * tq == 3 * n, dt3 = cb + 8 + 2 * tq + 1 == 3 * n;
+    const bool anydt = dt0 || dt1 || dt2 || dt3;
+    auto isdt = [&](int j, int e) { return j == 0 ? (e == 0 ? dt0 : dt1) : (e == 0 ? dt2 : dt3); };
+    const double *Xcol = Xs + 16 * w;  // this warp's 16 columns
     long u = blockIdx.x;
     if (u < a.cnt) { issue_A(u, 0); issue_B(u, 0); }
     for (; u < a.cnt; u += gridDim.x) {
         const double h = a.dt_u ? a.dt_u[u] : a.dt;
-        // X1 = identity on the (q, qd) columns: every warp initialises its own 32 columns (lane -> column 8 nt_{l/8} + l % 8)
-        {
-            const int ntc = w + 4 * (l >> 3), c = 8 * ntc + (l & 7);
-            if (ntc < NT)
-                for (int k = 0; k < K1; ++k) Xs[k * XS + c] = (k == c && k < 2 * n) ? 1.0 : 0.0;
-        }
-        __syncwarp();
-        double acc[MT][4][2], yv[MT][4][2];
+        double acc[MT][2][2], yv[MT][2][2], Pq[MT][2][2], AF[MT][2][2];
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
             const long un = u + gridDim.x;
@@ -510,128 +524,175 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_mma(TreeChainArgs a)
             const int s2 = s < 3 ? s + 1 : 0;
             cp_async_wait<1>();
             __syncthreads();
-            // ---- product 1 ----
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
-#pragma unroll 1
-            for (int ks = 0; ks < K1 / 4; ++ks) {
-                double af[MT], bf[4];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) af[mt] = DA[(8 * mt + g) * RSA + 4 * ks + tq];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bf[j] = (w + 4 * j < NT) ? Xs[(4 * ks + tq) * XS + 8 * (w + 4 * j) + g] : 0.0;
+            // ---- Z ----
+            if (s == 0) {  // X1 = unit columns: Z is a column of dID/dq (q columns), of dID/dqd (qd columns) or 0
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af[mt], bf[j]);
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = cb + 8 * j + 2 * tq + e;
+                            const int cc = c < n ? c : (c < 2 * n ? NR + c - n : -1);
+                            acc[mt][j][e] = cc >= 0 ? DA[(8 * mt + g) * RSA + cc] : 0.0;
+                        }
+            } else {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+                const double *ap = DA + g * RSA + tq, *bp = Xcol + tq * XS + g;
+                double af[MT], bf[2], af2[MT], bf2[2];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) af[mt] = ap[8 * mt * RSA];
+                bf[0] = bp[0]; bf[1] = bp[8];
+#pragma unroll 1
+                for (int ks = 0; ks < KS1; ks += 2) {  // two k-steps per trip, the next one's fragments loaded ahead of this one's DMMA
+                    const double *ap1 = ap + 4 * (ks + 1), *bp1 = bp + 4 * (ks + 1) * XS;
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) af2[mt] = ap1[8 * mt * RSA];
+                    bf2[0] = bp1[0]; bf2[1] = bp1[8];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) { dmma884(acc[mt][0][0], acc[mt][0][1], af[mt], bf[0]); dmma884(acc[mt][1][0], acc[mt][1][1], af[mt], bf[1]); }
+                    if (ks + 2 < KS1) {
+                        const double *ap2 = ap + 4 * (ks + 2), *bp2 = bp + 4 * (ks + 2) * XS;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) af[mt] = ap2[8 * mt * RSA];
+                        bf[0] = bp2[0]; bf[1] = bp2[8];
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) { dmma884(acc[mt][0][0], acc[mt][0][1], af2[mt], bf2[0]); dmma884(acc[mt][1][0], acc[mt][1][1], af2[mt], bf2[1]); }
+                }
             }
             __syncthreads();
             if (more) issue_A(u2, s2); else cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
-            // ---- rhs = E_tau - Z (element (r, c): r = 8 mt + g, c = 8 (w + 4 j) + 2 tq + e) ----
+            // ---- rhs = E_tau - Z ----
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
-                        acc[mt][j][e] = ((r < n && c == 2 * n + r) ? 1.0 : 0.0) - acc[mt][j][e];
-                    }
-            // ---- product 2: K = C rhs; B fragment (k = 4 ks + tq, col g) from lane 4 ((4 ks + tq) % 8) + g / 2, element g % 2 ----
+                    for (int e = 0; e < 2; ++e) acc[mt][j][e] = (((mt_ >> ((mt * 2 + j) * 2 + e)) & 1) ? 1.0 : 0.0) - acc[mt][j][e];
+            // ---- T = L^-T rhs: A(r, k) = L^-1[k][r], tiles with 4 ks + 3 >= 8 mt; B(k = 4 ks + tq, col g) sits in lane
+            //      4 (4 (ks & 1) + tq) + g / 2, element g % 2 of the m-tile ks / 2 of rhs ----
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0; }
+                for (int j = 0; j < 2; ++j) { yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0; }
 #pragma unroll
-            for (int ks = 0; ks < NR / 4; ++ks) {
-                double af[MT], bf[4];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) af[mt] = Cm[(8 * mt + g) * RSC + 4 * ks + tq];
+            for (int ks = 0; ks < KS2; ++ks) {
                 const int src = 4 * (4 * (ks & 1) + tq) + (g >> 1);
+                double bf[2];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                     const double v0 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][0], src), v1 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][1], src);
                     bf[j] = (g & 1) ? v1 : v0;
                 }
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                for (int mt = 0; mt <= ks / 2 && mt < MT; ++mt) {
+                    const double af = LI[(4 * ks + tq) * RSL + 8 * mt + g];
+                    dmma884(yv[mt][0][0], yv[mt][0][1], af, bf[0]);
+                    dmma884(yv[mt][1][0], yv[mt][1][1], af, bf[1]);
+                }
+            }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(yv[mt][j][0], yv[mt][j][1], af[mt], bf[j]);
+            for (int mt = 0; mt < MT; ++mt) {
+                const double di = DI[8 * mt + g];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { yv[mt][j][0] *= di; yv[mt][j][1] *= di; acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+            }
+            // ---- K = L^-1 T: A(r, k) = L^-1[r][k], tiles with 4 ks <= 8 mt + 7 ----
+#pragma unroll
+            for (int ks = 0; ks < KS2; ++ks) {
+                const int src = 4 * (4 * (ks & 1) + tq) + (g >> 1);
+                double bf[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const double v0 = __shfl_sync(0xffffffffu, yv[ks >> 1][j][0], src), v1 = __shfl_sync(0xffffffffu, yv[ks >> 1][j][1], src);
+                    bf[j] = (g & 1) ? v1 : v0;
+                }
+#pragma unroll
+                for (int mt = ks / 2; mt < MT; ++mt) {
+                    const double af = LI[(8 * mt + g) * RSL + 4 * ks + tq];
+                    dmma884(acc[mt][0][0], acc[mt][0][1], af, bf[0]);
+                    dmma884(acc[mt][1][0], acc[mt][1][1], af, bf[1]);
+                }
             }
             __syncthreads();
             if (more) issue_B(u2, s2); else cp_async_commit();
-            // ---- update ----
+            // ---- update: Yv, accumulators, next stage's X (warp-private columns) ----
             const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
             const double *Vs = V + (s & 1) * 4 * NR;
+            double *xw = Xs + 16 * w + 2 * tq;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int mt = 0; mt < MT; ++mt) {
+                const int r = 8 * mt + g;
+                const double fn = Vs[2 * NR + r];
+                const double qdd_r = anydt ? Vs[1 * NR + r] : 0.0, qd_r = anydt ? Vs[0 * NR + r] : 0.0, ex_r = Vs[3 * NR + r];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 2; ++j) {
+                    double2 xvold = make_double2(0.0, 0.0);
+                    if (s > 0) xvold = *reinterpret_cast<const double2 *>(xw + (NR + r) * XS + 8 * j);
+                    double xqn[2], xvn[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
-                        const int slot = ((mt * 4 + j) * 2 + e) * 128;
-                        if (r < n && c < NC) {
-                            const bool isdt = c == 3 * n;
-                            const double y = h * yv[mt][j][e] + (isdt ? Vs[1 * NR + r] : 0.0);
-                            yv[mt][j][e] = y;
-                            const double x1q = (c == r) ? 1.0 : 0.0, x1v = (c == n + r) ? 1.0 : 0.0;
-                            double *jcol = a.jac + (size_t)(isdt ? 4 * n : c) * a.UJ + u;
-                            if (s == 0) {
-                                jcol[(size_t)(n + r) * PC * a.UJ] = x1v - y * (1.0 / 6.0);
-                                Ps[slot] = y;
-                                AF[slot] = Vs[2 * NR + r] * y + (isdt ? Vs[3 * NR + r] : 0.0);
-                            } else if (s < 3) {
-                                atomicAdd(Ps + slot, y);
-                                atomicAdd(AF + slot, Vs[2 * NR + r] * y + ((s == 1 && c == n + r) ? Vs[3 * NR + r] : 0.0));
-                            }
-                            const double xvold = Xs[(n + r) * XS + c];
-                            const double yq = h * xvold + (isdt ? Vs[0 * NR + r] : 0.0);
-                            Xs[r * XS + c] = x1q + cs * yq;
-                            Xs[(n + r) * XS + c] = x1v + cs * y;
+                        const int bit = (mt * 2 + j) * 2 + e;
+                        const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
+                        const bool dtc = isdt(j, e);
+                        const double y = fma(h, acc[mt][j][e], dtc ? qdd_r : 0.0);
+                        acc[mt][j][e] = y;
+                        if (s == 0) {
+                            Pq[mt][j][e] = y;
+                            AF[mt][j][e] = fma(fn, y, dtc ? ex_r : 0.0);
+                        } else if (s < 3) {
+                            Pq[mt][j][e] += y;
+                            AF[mt][j][e] = fma(fn, y, AF[mt][j][e] + ((s == 1 && x1v != 0.0) ? ex_r : 0.0));
                         }
+                        const double xo = s > 0 ? (e == 0 ? xvold.x : xvold.y) : x1v;
+                        const double yq = fma(h, xo, dtc ? qd_r : 0.0);
+                        xqn[e] = fma(cs, yq, x1q);
+                        xvn[e] = fma(cs, y, x1v);
                     }
-            if (s == 3) {
-                // ---- epilogue: per m-tile, the scratch loads first (one round trip), then the stores ----
+                    if (s < 3) {
+                        *reinterpret_cast<double2 *>(xw + r * XS + 8 * j) = make_double2(xqn[0], xqn[1]);
+                        *reinterpret_cast<double2 *>(xw + (NR + r) * XS + 8 * j) = make_double2(xvn[0], xvn[1]);
+                    }
+                }
+            }
+            if (s == 0 || s == 3) {
+                // ---- Jacobian rows: after stage 1 the part of d qd+/dz that needs Yv_1 alone, after stage 4 everything else ----
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    double Pv[4][2], Av[4][2];
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
-                            const int slot = ((mt * 4 + j) * 2 + e) * 128;
-                            if (r < n && c < NC) { Pv[j][e] = Ps[slot]; Av[j][e] = AF[slot]; }
-                        }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const int r = 8 * mt + g, c = 8 * (w + 4 * j) + 2 * tq + e;
+                            const int r = 8 * mt + g, c = cb + 8 * j + 2 * tq + e, bit = (mt * 2 + j) * 2 + e;
                             if (r < n && c < NC) {
-                                const bool isdt = c == 3 * n;
-                                const double x1q = (c == r) ? 1.0 : 0.0, x1v = (c == n + r) ? 1.0 : 0.0;
-                                double *jcol = a.jac + (size_t)(isdt ? 4 * n : c) * a.UJ + u;
-                                jcol[(size_t)r * PC * a.UJ] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pv[j][e] + (isdt ? Vs[3 * NR + r] : 0.0);
-                                atomicAdd(jcol + (size_t)(n + r) * PC * a.UJ, (2.0 * Pv[j][e] + yv[mt][j][e]) * (1.0 / 6.0));
-                                double afv = Av[j][e];
-                                if (c == 2 * n + r) {
-                                    const double z = a.fat[4 * r] * h;
-                                    afv += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                                const bool dtc = isdt(j, e);
+                                const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
+                                double *jcol = a.jac + (size_t)(dtc ? 4 * n : c) * a.UJ + u;
+                                if (s == 0) {
+                                    jcol[(size_t)(n + r) * PC * a.UJ] = x1v - acc[mt][j][e] * (1.0 / 6.0);
+                                } else {
+                                    jcol[(size_t)r * PC * a.UJ] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pq[mt][j][e] + (dtc ? Vs[3 * NR + r] : 0.0);
+                                    red_add(jcol + (size_t)(n + r) * PC * a.UJ, (2.0 * Pq[mt][j][e] + acc[mt][j][e]) * (1.0 / 6.0));
+                                    double afv = AF[mt][j][e];
+                                    if ((mt_ >> bit) & 1) {
+                                        const double z = a.fat[4 * r] * h;
+                                        afv += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                                    }
+                                    jcol[(size_t)(2 * n + r) * PC * a.UJ] = afv;
                                 }
-                                jcol[(size_t)(2 * n + r) * PC * a.UJ] = afv;
                             }
                         }
-                }
             }
             __syncwarp();
         }
-        for (int idx = t; idx < 3 * n * n; idx += 128) {
+        // ---- the n fatigue columns in closed form, shared between the slabs ----
+        for (int idx = t + 128 * slab; idx < 3 * n * n; idx += 128 * nslab) {
             const int r = idx / n, j = idx - r * n;
             double v = 0.0;
             if (r == 2 * n + j) {
@@ -649,11 +710,6 @@ static std::atomic<bool> g_tree_attr[64];
 
 bool tree_jvp_supported(const LaunchModel &m) { return (m.fam == FAM_GENERIC16 || m.fam == FAM_GENERIC64) && m.n <= 40; }
 
-static size_t tree_chain_mma_smem(int NR, int npat)
-{
-    const int RSA = 2 * NR - 4, RSC = NR + 4, XS = 116;
-    return ((size_t)NR * RSA + (size_t)NR * RSC + 2 * 4 * NR + (size_t)RSA * XS) * sizeof(double) + (size_t)2 * npat * sizeof(unsigned short);
-}
 static size_t tree_chain_smem(int n, int NR, int npat)
 {
     const int NC = 3 * n + 1, XS = (NC + 15) & ~15;
@@ -677,7 +733,9 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tree_chain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_tree_chain_mma<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024);
+        e = cudaFuncSetAttribute(k_tree_chain_tc<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tree_chain_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         if (e != cudaSuccess) return e;
         g_tree_attr[dev].store(true, std::memory_order_release);
     }
@@ -697,18 +755,21 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         const unsigned gb = (unsigned)((c + kThreads - 1) / kThreads);
         k_tree_stages<MAXN><<<gb, kThreads, smem12, s>>>(m.blob, W, U, c, q + u0, qd + u0, tau + u0, f + u0, dt, dt_u ? dt_u + u0 : nullptr,
                                                         qn ? qn + u0 : nullptr, qdn ? qdn + u0 : nullptr, fn ? fn + u0 : nullptr, ws);
-        // MPCF_TREE_MMA=1 selects the FP64 tensor-core chain kernel (n in 17..37).  Measured on the 37-joint tree: 18.6 ms per 33k
-        // units against 19.5 ms for the scalar kernel, but it needs M^-1 from k_tree_derivs, which costs 13 ms more than the
-        // factor alone (latency-bound sparse solves in local memory), so the scalar kernel is the default (profiles/r02_c4.md).
-        const char *env = getenv("MPCF_TREE_MMA");
-        const bool use_mma = env && atoi(env) != 0 && NR == 40 && n > 16 && n <= 37 && tree_chain_mma_smem(40, npat) <= 113 * 1024;
-        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_mma ? 1 : 0);
+        // default: the tensor-core chain kernel; MPCF_TREE_CHAIN=scalar selects the DFMA kernel (kept as a cross-check: same
+        // recursion with triangular solves instead of the products with L^-1)
+        const char *env = getenv("MPCF_TREE_CHAIN");
+        const bool use_tc = !(env && env[0] == 's');
+        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_tc ? 1 : 0);
         TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
-        const unsigned g3 = (unsigned)(c < grid3_max ? c : grid3_max);
-        if (use_mma)
-            k_tree_chain_mma<40><<<g3, 128, tree_chain_mma_smem(40, npat), s>>>(a);
-        else
+        if (use_tc) {
+            const int nslab = (3 * n + 1 + 63) / 64;
+            const long gx_max = (long)nsm * 2 / nslab;
+            const unsigned gx = (unsigned)(c < gx_max ? c : gx_max);
+            k_tree_chain_tc<NR><<<dim3(gx, nslab), 128, TcLayout<NR>::bytes(npat), s>>>(a);
+        } else {
+            const unsigned g3 = (unsigned)(c < grid3_max ? c : grid3_max);
             k_tree_chain<NR><<<g3, 128, smem3, s>>>(a);
+        }
         g_launches.fetch_add(3);
     }
     return cudaGetLastError();

@@ -172,6 +172,26 @@ struct TreeDerivs {
             x[i] = s;
         }
     }
+    // In place, after factorize(): the strictly-lower entries L_kj become those of L^-1 (unit lower triangular on the SAME
+    // ancestor pattern: the ancestor relation is transitive, so inverting creates no fill-in); the diagonal keeps D_k.
+    // Then M^-1 = L^-1 D^-1 L^-T is two triangular PRODUCTS instead of two solves (k_tree_chain_tc).  Row i, ancestor at depth
+    // d:  Linv_id = -L_id - sum_{d < e < depth(i)} L_ie Linv_{anc_e(i), d};  rows in ascending order (ancestors come first).
+    // path, lrow: caller scratch [n].
+    static MPCF_HD void invert_unit_factor(const MP &m, double *Mp, int *path, double *lrow)
+    {
+        const int n = m.n();
+        for (int i = 0; i < n; ++i) {
+            const int di = m.depth(i), ri = m.rowptr(i);
+            if (di == 0) continue;
+            for (int a = m.parent(i); a >= 0; a = m.parent(a)) path[m.depth(a)] = a;
+            for (int d = 0; d < di; ++d) lrow[d] = Mp[ri + d];
+            for (int d = di - 1; d >= 0; --d) {
+                double s = -lrow[d];
+                for (int e = d + 1; e < di; ++e) s -= lrow[e] * Mp[m.rowptr(path[e]) + d];
+                Mp[ri + d] = s;
+            }
+        }
+    }
     static MPCF_HD double nan_value_hd()
     {
         const double zero = 0.0;

@@ -1,0 +1,11 @@
+#!/bin/bash
+set -u
+O=gpurun_out/r02i; mkdir -p $O
+ncu --set full --clock-control none --import-source on -k regex:"k_tree_chain" -s 1 -c 1 -o $O/t3 python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/ncu_f.log 2>&1
+ncu -i $O/t3.ncu-rep --page raw --csv > $O/t3_raw.csv 2>/dev/null
+ncu -i $O/t3.ncu-rep --page source --csv > $O/t3_src.csv 2>/dev/null
+rm -f $O/t3.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:"k_tree_derivs" -s 1 -c 1 -o $O/t2 python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/ncu_f2.log 2>&1
+ncu -i $O/t2.ncu-rep --page raw --csv > $O/t2_raw.csv 2>/dev/null
+ncu -i $O/t2.ncu-rep --page source --csv > $O/t2_src.csv 2>/dev/null
+rm -f $O/t2.ncu-rep; ls -la $O

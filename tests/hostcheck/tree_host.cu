@@ -83,6 +83,27 @@ extern "C" int hc_tree_derivs(int n, const int *parent, const int *jtype, const 
     return ok ? 0 : -1;
 }
 
+// Linv dense [n][n]: the unit lower-triangular inverse of L from invert_unit_factor (diagonal: D_k, as in Lfac)
+extern "C" int hc_tree_linv(int n, const int *parent, const int *jtype, const double *Rp, const double *pp, const double *mass, const double *mc,
+                            const double *Io, const double *arm, const double *grav, const double *q, const double *qd, const double *qdd, double *Linv)
+{
+    Topo tp(n, parent);
+    HostTree m{n, parent, jtype, tp.depth.data(), tp.rowptr.data(), Rp, pp, mass, mc, Io, arm, grav};
+    std::vector<TreeRec> rec(n);
+    std::vector<TreeComp> comp(n);
+    std::vector<double> Mp(tp.rowptr[n]), Dq(n * n), Dv(n * n), lrow(n);
+    std::vector<int> path(n);
+    DenseOut out{n, Dq.data(), Dv.data()};
+    TreeDerivs<HostTree>::forward(m, q, qd, qdd, rec.data());
+    TreeDerivs<HostTree>::backward(m, rec.data(), comp.data(), Mp.data(), out);
+    const bool ok = TreeDerivs<HostTree>::factorize(m, Mp.data());
+    TreeDerivs<HostTree>::invert_unit_factor(m, Mp.data(), path.data(), lrow.data());
+    std::memset(Linv, 0, sizeof(double) * n * n);
+    for (int k = 0; k < n; ++k)
+        for (int j = k; j >= 0; j = parent[j]) Linv[k * n + j] = Mp[tp.rowptr[k] + tp.depth[j]];
+    return ok ? 0 : -1;
+}
+
 // The column recursion of kernels_tree.cu (k_tree_chain) as plain loops.  Inputs per stage s = 0..3: dense Dq_s, Dv_s, Lfac_s
 // (as returned above), qd_s, qdd_s, fdot_s; fat[n][4] = (lambda, kappa, ctau, cv); tau[n]; step h.  Output jac[3n][4n+1].
 extern "C" void hc_tree_chain(int n, const double *Dq, const double *Dv, const double *Lfac, const double *qds, const double *qdds,

@@ -1,4 +1,4 @@
-"""GPU: the run-time-tree Jacobian pipeline (csrc/kernels_tree.cu: k_tree_stages -> k_tree_derivs -> k_tree_chain) against the
+"""GPU: the run-time-tree Jacobian pipeline (csrc/kernels_tree.cu: k_tree_stages -> k_tree_derivs -> k_tree_chain_tc) against the
 oracle's complex-step Jacobian, per Jacobian plane, on the 37-joint branched tree of config C4 (prismatic + revolute root
 chain, six limbs), a short chain and the mixed-joint URDF; ragged batches, per-unit dt, dt = 0, workspace chunking, and
 agreement with the dual-number sweeps it replaces."""
@@ -105,10 +105,12 @@ def test_c4_sample_of_the_full_size_batch():
     assert rel_err_rows(gj.reshape(-1, U), rj.reshape(-1, U)) < TOL
 
 
-def test_tensor_core_chain_kernel_matches_the_oracle(monkeypatch):
-    """MPCF_TREE_MMA=1: the same recursion with both per-stage products on the FP64 tensor cores (mma.sync m8n8k4, the second
-    product's B operand shuffled out of the first one's accumulator fragments) and M^-1 from k_tree_derivs."""
-    monkeypatch.setenv("MPCF_TREE_MMA", "1")
-    _check(MODELS["humanoid37"](), 130, 0.0125, seed=46)
-    dt_u = np.ascontiguousarray(np.random.default_rng(2).uniform(0.002, 0.02, 33))
-    _check(MODELS["humanoid37"](), 33, 0.0, seed=47, dt_u=dt_u)
+@pytest.mark.parametrize("name", ["humanoid37", "chain9", "chain40", "mixed"])
+def test_scalar_chain_kernel_matches_the_oracle(monkeypatch, name):
+    """MPCF_TREE_CHAIN=scalar: the DFMA chain kernel (triangular solves with L instead of the tensor-core products with L^-1) is
+    kept as an independent cross-check of the default path; both must agree with the oracle."""
+    monkeypatch.setenv("MPCF_TREE_CHAIN", "scalar")
+    _check(MODELS[name](), 33 if name == "chain40" else 130, 0.0125, seed=46)
+    if name == "humanoid37":
+        dt_u = np.ascontiguousarray(np.random.default_rng(2).uniform(0.002, 0.02, 33))
+        _check(MODELS[name](), 33, 0.0, seed=47, dt_u=dt_u)

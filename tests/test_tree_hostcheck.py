@@ -73,6 +73,13 @@ def test_tree_id_derivatives_and_factorisation(lib, name):
         L = np.tril(Lf, -1) + np.eye(n)
         D = np.diag(np.diag(Lf))
         assert np.abs(L.T @ D @ L - M).max() < 1e-11 * np.abs(M).max()
+        # the in-place inverse of the unit factor (what the tensor-core chain kernel multiplies by): same pattern, L^-1 L = 1
+        Li = np.zeros((n, n))
+        assert lib.hc_tree_linv(*margs, _p(np.ascontiguousarray(q[:, u])), _p(np.ascontiguousarray(qd[:, u])), _p(np.ascontiguousarray(qdd[:, u])), _p(Li)) == 0
+        assert np.array_equal(np.diag(Li), np.diag(Lf)) and np.array_equal(Li != 0, Lf != 0)
+        Linv = np.tril(Li, -1) + np.eye(n)
+        assert np.abs(Linv @ L - np.eye(n)).max() < 1e-12
+        assert np.abs(Linv @ np.diag(1.0 / np.diag(Lf)) @ Linv.T @ M - np.eye(n)).max() < 1e-9
         for k in range(n):  # no fill-in outside the pattern
             anc, j = set(), par[k]
             while j >= 0:
