@@ -434,7 +434,7 @@ MPCF_DI void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0
 template <int NR>
 struct TcLayout {
     static constexpr int MT = NR / 8, RSA = 2 * NR + 4, RSL = NR + 4, XS = 68, KS1 = NR / 2, KS2 = NR / 4;
-    static constexpr int oDA = 0, oLI = oDA + NR * RSA, oDI = oLI + NR * RSL, oV = oDI + NR, oX = oV + 2 * 4 * NR, nD = oX + 2 * NR * XS;
+    static constexpr int oDA = 0, oLI = oDA + NR * RSA, oDI = oLI + NR * RSL, oV = oDI + NR, oTF = oV + 2 * 4 * NR, oX = oTF + NR, nD = oX + 2 * NR * XS;
     static size_t bytes(int npat) { return (size_t)nD * sizeof(double) + (size_t)3 * npat * sizeof(unsigned short); }
 };
 
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
     const int n = W.n, npat = W.npat;
     const int NC = 3 * n + 1;
     extern __shared__ __align__(16) double sm[];
-    double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *Xs = sm + Ly::oX;
+    double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *TF = sm + Ly::oTF, *Xs = sm + Ly::oX;
     unsigned short *okj = reinterpret_cast<unsigned short *>(sm + Ly::nD), *ojk = okj + npat, *okl = ojk + npat;
     const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
     const int slab = blockIdx.y, nslab = gridDim.y;
@@ -511,19 +511,36 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
     const bool anydt = dt0 || dt1 || dt2 || dt3;
     auto isdt = [&](int j, int e) { return j == 0 ? (e == 0 ? dt0 : dt1) : (e == 0 ? dt2 : dt3); };
     const double *Xcol = Xs + 16 * w;  // this warp's 16 columns
-    long u = blockIdx.x;
+    // Units are handed out dynamically (one counter per slab, zeroed by the launcher) instead of strided by CTA: units u .. u + 3
+    // share every 32-byte sector of the AoSoA workspace and of the [plane][unit] Jacobian, and only units that are in flight at
+    // about the same time meet in L2 (with a static stride the CTAs drift apart: 36 GB of DRAM reads per 32k units instead of 5).
+    __shared__ unsigned long long s_unit[2];
+    unsigned long long *counter = reinterpret_cast<unsigned long long *>(a.scratch) + slab;
+    if (t == 0) s_unit[0] = atomicAdd(counter, 1ull);
+    __syncthreads();
+    long u = (long)s_unit[0];
+    int par = 0;
     if (u < a.cnt) { issue_A(u, 0); issue_B(u, 0); }
-    for (; u < a.cnt; u += gridDim.x) {
+    for (; u < a.cnt; par ^= 1) {
+        if (t == 0) s_unit[par ^ 1] = atomicAdd(counter, 1ull);  // the unit after this one: read behind the stage barriers
+        long un = a.cnt;
         const double h = a.dt_u ? a.dt_u[u] : a.dt;
+        // closed-form tau-column term of the fatigue rows (row r, column tau_r), one value per joint
+        double tf = 0.0;
+        if (t < n) {
+            const double z = a.fat[4 * t] * h;
+            tf = 2.0 * a.fat[4 * t + 1] * a.fat[4 * t + 2] * a.tau[(size_t)t * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+        }
         double acc[MT][2][2], yv[MT][2][2], Pq[MT][2][2], AF[MT][2][2];
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
-            const long un = u + gridDim.x;
+            cp_async_wait<1>();
+            __syncthreads();
+            if (s == 3) un = (long)s_unit[par ^ 1];
             const bool more = s < 3 || un < a.cnt;
             const long u2 = s < 3 ? u : un;
             const int s2 = s < 3 ? s + 1 : 0;
-            cp_async_wait<1>();
-            __syncthreads();
+            if (s == 0 && t < n) TF[t] = tf;  // every warp has left the previous unit's epilogue; read after many barriers
             // ---- Z ----
             if (s == 0) {  // X1 = unit columns: Z is a column of dID/dq (q columns), of dID/dqd (qd columns) or 0
 #pragma unroll
@@ -568,64 +585,59 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             if (more) issue_A(u2, s2); else cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
-            // ---- rhs = E_tau - Z ----
+            // ---- rhs = E_tau - Z, staged in this warp's (dead) X[q] rows so that the next product reads its B fragments with the same
+            //      conflict-free loads as the first one ----
+            double *xw = Xs + 16 * w + 2 * tq;
+            const double *bq = Xcol + tq * XS + g;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) acc[mt][j][e] = (((mt_ >> ((mt * 2 + j) * 2 + e)) & 1) ? 1.0 : 0.0) - acc[mt][j][e];
-            // ---- T = L^-T rhs: A(r, k) = L^-1[k][r], tiles with 4 ks + 3 >= 8 mt; B(k = 4 ks + tq, col g) sits in lane
-            //      4 (4 (ks & 1) + tq) + g / 2, element g % 2 of the m-tile ks / 2 of rhs ----
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) { yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0; }
-#pragma unroll
-            for (int ks = 0; ks < KS2; ++ks) {
-                const int src = 4 * (4 * (ks & 1) + tq) + (g >> 1);
-                double bf[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const double v0 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][0], src), v1 = __shfl_sync(0xffffffffu, acc[ks >> 1][j][1], src);
-                    bf[j] = (g & 1) ? v1 : v0;
+                    const double r0 = (((mt_ >> ((mt * 2 + j) * 2)) & 1) ? 1.0 : 0.0) - acc[mt][j][0];
+                    const double r1 = (((mt_ >> ((mt * 2 + j) * 2 + 1)) & 1) ? 1.0 : 0.0) - acc[mt][j][1];
+                    *reinterpret_cast<double2 *>(xw + (8 * mt + g) * XS + 8 * j) = make_double2(r0, r1);
+                    yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0;
                 }
+            __syncwarp();
+            // ---- T = D^-1 L^-T rhs: A(r, k) = L^-1[k][r], only the tiles with 4 ks + 3 >= 8 mt ----
+#pragma unroll
+            for (int ks = 0; ks < KS2; ++ks) {
+                const double b0 = bq[4 * ks * XS], b1 = bq[4 * ks * XS + 8];
 #pragma unroll
                 for (int mt = 0; mt <= ks / 2 && mt < MT; ++mt) {
                     const double af = LI[(4 * ks + tq) * RSL + 8 * mt + g];
-                    dmma884(yv[mt][0][0], yv[mt][0][1], af, bf[0]);
-                    dmma884(yv[mt][1][0], yv[mt][1][1], af, bf[1]);
+                    dmma884(yv[mt][0][0], yv[mt][0][1], af, b0);
+                    dmma884(yv[mt][1][0], yv[mt][1][1], af, b1);
                 }
             }
+            __syncwarp();
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const double di = DI[8 * mt + g];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) { yv[mt][j][0] *= di; yv[mt][j][1] *= di; acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+                for (int j = 0; j < 2; ++j) {
+                    *reinterpret_cast<double2 *>(xw + (8 * mt + g) * XS + 8 * j) = make_double2(yv[mt][j][0] * di, yv[mt][j][1] * di);
+                    acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0;
+                }
             }
-            // ---- K = L^-1 T: A(r, k) = L^-1[r][k], tiles with 4 ks <= 8 mt + 7 ----
+            __syncwarp();
+            // ---- K = L^-1 T: A(r, k) = L^-1[r][k], only the tiles with 4 ks <= 8 mt + 7 ----
 #pragma unroll
             for (int ks = 0; ks < KS2; ++ks) {
-                const int src = 4 * (4 * (ks & 1) + tq) + (g >> 1);
-                double bf[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const double v0 = __shfl_sync(0xffffffffu, yv[ks >> 1][j][0], src), v1 = __shfl_sync(0xffffffffu, yv[ks >> 1][j][1], src);
-                    bf[j] = (g & 1) ? v1 : v0;
-                }
+                const double b0 = bq[4 * ks * XS], b1 = bq[4 * ks * XS + 8];
 #pragma unroll
                 for (int mt = ks / 2; mt < MT; ++mt) {
                     const double af = LI[(8 * mt + g) * RSL + 4 * ks + tq];
-                    dmma884(acc[mt][0][0], acc[mt][0][1], af, bf[0]);
-                    dmma884(acc[mt][1][0], acc[mt][1][1], af, bf[1]);
+                    dmma884(acc[mt][0][0], acc[mt][0][1], af, b0);
+                    dmma884(acc[mt][1][0], acc[mt][1][1], af, b1);
                 }
             }
+            __syncwarp();
             __syncthreads();
             if (more) issue_B(u2, s2); else cp_async_commit();
             // ---- update: Yv, accumulators, next stage's X (warp-private columns) ----
             const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
             const double *Vs = V + (s & 1) * 4 * NR;
-            double *xw = Xs + 16 * w + 2 * tq;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int r = 8 * mt + g;
@@ -662,47 +674,56 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                 }
             }
             if (s == 0 || s == 3) {
-                // ---- Jacobian rows: after stage 1 the part of d qd+/dz that needs Yv_1 alone, after stage 4 everything else ----
+                // ---- Jacobian rows: after stage 1 the part of d qd+/dz that needs Yv_1 alone, after stage 4 everything else.
+                //      Column by column: one pointer per column, stepped by 8 rows per m-tile ----
+                const size_t RSJ = (size_t)PC * a.UJ;  // one Jacobian row (all columns, plane stride UJ)
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = cb + 8 * j + 2 * tq + e;
+                        const bool dtc = isdt(j, e);
+                        if (c < NC) {
+                            double *p = a.jac + (size_t)(dtc ? 4 * n : c) * a.UJ + u + (size_t)g * RSJ;
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int r = 8 * mt + g, c = cb + 8 * j + 2 * tq + e, bit = (mt * 2 + j) * 2 + e;
-                            if (r < n && c < NC) {
-                                const bool dtc = isdt(j, e);
-                                const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
-                                double *jcol = a.jac + (size_t)(dtc ? 4 * n : c) * a.UJ + u;
-                                if (s == 0) {
-                                    jcol[(size_t)(n + r) * PC * a.UJ] = x1v - acc[mt][j][e] * (1.0 / 6.0);
-                                } else {
-                                    jcol[(size_t)r * PC * a.UJ] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pq[mt][j][e] + (dtc ? Vs[3 * NR + r] : 0.0);
-                                    red_add(jcol + (size_t)(n + r) * PC * a.UJ, (2.0 * Pq[mt][j][e] + acc[mt][j][e]) * (1.0 / 6.0));
-                                    double afv = AF[mt][j][e];
-                                    if ((mt_ >> bit) & 1) {
-                                        const double z = a.fat[4 * r] * h;
-                                        afv += 2.0 * a.fat[4 * r + 1] * a.fat[4 * r + 2] * a.tau[(size_t)r * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
+                            for (int mt = 0; mt < MT; ++mt, p += 8 * RSJ) {
+                                const int r = 8 * mt + g, bit = (mt * 2 + j) * 2 + e;
+                                if (r < n) {
+                                    const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
+                                    if (s == 0) {
+                                        p[(size_t)n * RSJ] = x1v - acc[mt][j][e] * (1.0 / 6.0);
+                                    } else {
+                                        p[0] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pq[mt][j][e] + (dtc ? Vs[3 * NR + r] : 0.0);
+                                        red_add(p + (size_t)n * RSJ, (2.0 * Pq[mt][j][e] + acc[mt][j][e]) * (1.0 / 6.0));
+                                        p[(size_t)2 * n * RSJ] = AF[mt][j][e] + (((mt_ >> bit) & 1) ? TF[r] : 0.0);
                                     }
-                                    jcol[(size_t)(2 * n + r) * PC * a.UJ] = afv;
                                 }
                             }
                         }
+                    }
             }
             __syncwarp();
         }
-        // ---- the n fatigue columns in closed form, shared between the slabs ----
-        for (int idx = t + 128 * slab; idx < 3 * n * n; idx += 128 * nslab) {
-            const int r = idx / n, j = idx - r * n;
-            double v = 0.0;
-            if (r == 2 * n + j) {
-                const double z = a.fat[4 * j] * h;
-                v = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
-            }
-            a.jac[((size_t)r * PC + 3 * n + j) * a.UJ + u] = v;
-        }
+        u = un;
     }
     cp_async_wait<0>();
+}
+
+// The n fatigue columns of the Jacobian in closed form (d(q+, qd+)/df = 0, df+/df = diag of the RK4 amplification of the linear
+// fatigue rows): 3n x n planes per unit, written coalesced (thread = unit, blockIdx.y = Jacobian row) beside the chain kernel.
+__global__ void __launch_bounds__(256) k_tree_fill_fatigue_cols(int n, long cnt, long UJ, const double *fat, double dt, const double *dt_u, double *jac)
+{
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= cnt) return;
+    const int r = blockIdx.y;
+    const long PC = 4 * n + 1;
+    double *p = jac + ((size_t)r * PC + 3 * n) * UJ + u;
+    double v = 0.0;
+    if (r >= 2 * n) {
+        const double z = fat[4 * (r - 2 * n)] * (dt_u ? dt_u[u] : dt);
+        v = 1.0 + z * (-1.0 + z * (0.5 + z * (-1.0 / 6.0 + z * (1.0 / 24.0))));
+    }
+    for (int j = 0; j < n; ++j) __stcs(p + (size_t)j * UJ, (j == r - 2 * n) ? v : 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -765,7 +786,10 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
             const int nslab = (3 * n + 1 + 63) / 64;
             const long gx_max = (long)nsm * 2 / nslab;
             const unsigned gx = (unsigned)(c < gx_max ? c : gx_max);
+            cudaMemsetAsync(scratch, 0, 64, s);  // the per-slab unit counters
             k_tree_chain_tc<NR><<<dim3(gx, nslab), 128, TcLayout<NR>::bytes(npat), s>>>(a);
+            k_tree_fill_fatigue_cols<<<dim3((unsigned)((c + 255) / 256), 3 * n), 256, 0, s>>>(n, c, UJ, a.fat, dt, a.dt_u, a.jac);
+            g_launches.fetch_add(1);
         } else {
             const unsigned g3 = (unsigned)(c < grid3_max ? c : grid3_max);
             k_tree_chain<NR><<<g3, 128, smem3, s>>>(a);
