@@ -434,7 +434,7 @@ MPCF_DI void red_add(double *p, double v) { asm volatile("red.global.add.f64 [%0
 template <int NR>
 struct TcLayout {
     static constexpr int MT = NR / 8, RSA = 2 * NR + 4, RSL = NR + 4, XS = 68, KS1 = NR / 2, KS2 = NR / 4;
-    static constexpr int oDA = 0, oLI = oDA + NR * RSA, oDI = oLI + NR * RSL, oV = oDI + NR, oTF = oV + 2 * 4 * NR, oX = oTF + NR, nD = oX + 2 * NR * XS;
+    static constexpr int oDA = 0, oLI = oDA + NR * RSA, oDI = oLI + NR * RSL, oV = oDI + NR, oTF = oV + 2 * 4 * NR, oX = oTF + NR, oY1 = oX + 2 * NR * XS, nD = oY1 + 4 * MT * 128;
     static size_t bytes(int npat) { return (size_t)nD * sizeof(double) + (size_t)3 * npat * sizeof(unsigned short); }
 };
 
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
     const int n = W.n, npat = W.npat;
     const int NC = 3 * n + 1;
     extern __shared__ __align__(16) double sm[];
-    double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *TF = sm + Ly::oTF, *Xs = sm + Ly::oX;
+    double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *TF = sm + Ly::oTF, *Xs = sm + Ly::oX, *Y1 = sm + Ly::oY1;
     unsigned short *okj = reinterpret_cast<unsigned short *>(sm + Ly::nD), *ojk = okj + npat, *okl = ojk + npat;
     const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
     const int slab = blockIdx.y, nslab = gridDim.y;
@@ -508,7 +508,15 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                 if (r < n && c == 2 * n + r) mt_ |= 1u << bit;
             }
     const bool dt0 = cb + 2 * tq == 3 * n, dt1 = cb + 2 * tq + 1 == 3 * n, dt2 = cb + 8 + 2 * tq == 3 * n, dt3 = cb + 8 + 2 * tq + 1 == 3 * n;
-    const bool anydt = dt0 || dt1 || dt2 || dt3;
+    unsigned sp = 0;  // bit mt * 2 + j: some lane of this warp has a special entry in tile (mt, j) -> warp-uniform
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int tile = mt * 2 + j;
+            const bool mine = (((mq | mv | mt_) >> (tile * 2)) & 3u) != 0 || (j == 0 ? (dt0 || dt1) : (dt2 || dt3));
+            if (__any_sync(0xffffffffu, mine)) sp |= 1u << tile;
+        }
     auto isdt = [&](int j, int e) { return j == 0 ? (e == 0 ? dt0 : dt1) : (e == 0 ? dt2 : dt3); };
     const double *Xcol = Xs + 16 * w;  // this warp's 16 columns
     // Units are handed out dynamically (one counter per slab, zeroed by the launcher) instead of strided by CTA: units u .. u + 3
@@ -635,37 +643,59 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             __syncwarp();
             __syncthreads();
             if (more) issue_B(u2, s2); else cp_async_commit();
-            // ---- update: Yv, accumulators, next stage's X (warp-private columns) ----
+            // ---- update: Yv, accumulators, next stage's X (warp-private columns).  Per 8 x 8 tile one warp-uniform branch: only the
+            //      few tiles that hold a unit entry of X1, a tau-column unit entry or the dt column take the general form ----
             const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
+            const double csh = cs * h;
             const double *Vs = V + (s & 1) * 4 * NR;
+            double *y1 = Y1 + t;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int r = 8 * mt + g;
                 const double fn = Vs[2 * NR + r];
-                const double qdd_r = anydt ? Vs[1 * NR + r] : 0.0, qd_r = anydt ? Vs[0 * NR + r] : 0.0, ex_r = Vs[3 * NR + r];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
+                    const int tile = mt * 2 + j;
                     double2 xvold = make_double2(0.0, 0.0);
                     if (s > 0) xvold = *reinterpret_cast<const double2 *>(xw + (NR + r) * XS + 8 * j);
                     double xqn[2], xvn[2];
+                    if ((sp >> tile) & 1) {
+                        const double qdd_r = Vs[1 * NR + r], qd_r = Vs[0 * NR + r], ex_r = Vs[3 * NR + r];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int bit = (mt * 2 + j) * 2 + e;
-                        const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
-                        const bool dtc = isdt(j, e);
-                        const double y = fma(h, acc[mt][j][e], dtc ? qdd_r : 0.0);
-                        acc[mt][j][e] = y;
-                        if (s == 0) {
-                            Pq[mt][j][e] = y;
-                            AF[mt][j][e] = fma(fn, y, dtc ? ex_r : 0.0);
-                        } else if (s < 3) {
-                            Pq[mt][j][e] += y;
-                            AF[mt][j][e] = fma(fn, y, AF[mt][j][e] + ((s == 1 && x1v != 0.0) ? ex_r : 0.0));
+                        for (int e = 0; e < 2; ++e) {
+                            const int bit = tile * 2 + e;
+                            const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
+                            const bool dtc = isdt(j, e);
+                            const double y = fma(h, acc[mt][j][e], dtc ? qdd_r : 0.0);
+                            acc[mt][j][e] = y;
+                            if (s == 0) {
+                                Pq[mt][j][e] = y;
+                                AF[mt][j][e] = fma(fn, y, dtc ? ex_r : 0.0);
+                                y1[bit * 128] = y;
+                            } else if (s < 3) {
+                                Pq[mt][j][e] += y;
+                                AF[mt][j][e] = fma(fn, y, AF[mt][j][e] + ((s == 1 && x1v != 0.0) ? ex_r : 0.0));
+                            }
+                            const double xo = s > 0 ? (e == 0 ? xvold.x : xvold.y) : x1v;
+                            xqn[e] = fma(cs, fma(h, xo, dtc ? qd_r : 0.0), x1q);
+                            xvn[e] = fma(cs, y, x1v);
                         }
-                        const double xo = s > 0 ? (e == 0 ? xvold.x : xvold.y) : x1v;
-                        const double yq = fma(h, xo, dtc ? qd_r : 0.0);
-                        xqn[e] = fma(cs, yq, x1q);
-                        xvn[e] = fma(cs, y, x1v);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double y = h * acc[mt][j][e];
+                            acc[mt][j][e] = y;
+                            if (s == 0) {
+                                Pq[mt][j][e] = y;
+                                AF[mt][j][e] = fn * y;
+                                y1[(tile * 2 + e) * 128] = y;
+                            } else if (s < 3) {
+                                Pq[mt][j][e] += y;
+                                AF[mt][j][e] = fma(fn, y, AF[mt][j][e]);
+                            }
+                            xqn[e] = csh * (e == 0 ? xvold.x : xvold.y);
+                            xvn[e] = cs * y;
+                        }
                     }
                     if (s < 3) {
                         *reinterpret_cast<double2 *>(xw + r * XS + 8 * j) = make_double2(xqn[0], xqn[1]);
@@ -673,10 +703,10 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                     }
                 }
             }
-            if (s == 0 || s == 3) {
-                // ---- Jacobian rows: after stage 1 the part of d qd+/dz that needs Yv_1 alone, after stage 4 everything else.
-                //      Column by column: one pointer per column, stepped by 8 rows per m-tile ----
+            if (s == 3) {
+                // ---- Jacobian rows, column by column: one pointer per column, stepped by 8 rows per m-tile ----
                 const size_t RSJ = (size_t)PC * a.UJ;  // one Jacobian row (all columns, plane stride UJ)
+                const double h6 = h * (1.0 / 6.0);
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -687,16 +717,20 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                             double *p = a.jac + (size_t)(dtc ? 4 * n : c) * a.UJ + u + (size_t)g * RSJ;
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt, p += 8 * RSJ) {
-                                const int r = 8 * mt + g, bit = (mt * 2 + j) * 2 + e;
+                                const int r = 8 * mt + g, tile = mt * 2 + j, bit = tile * 2 + e;
                                 if (r < n) {
-                                    const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
-                                    if (s == 0) {
-                                        p[(size_t)n * RSJ] = x1v - acc[mt][j][e] * (1.0 / 6.0);
-                                    } else {
-                                        p[0] = x1q + h * x1v + (h * (1.0 / 6.0)) * Pq[mt][j][e] + (dtc ? Vs[3 * NR + r] : 0.0);
-                                        red_add(p + (size_t)n * RSJ, (2.0 * Pq[mt][j][e] + acc[mt][j][e]) * (1.0 / 6.0));
-                                        p[(size_t)2 * n * RSJ] = AF[mt][j][e] + (((mt_ >> bit) & 1) ? TF[r] : 0.0);
+                                    double jq = h6 * Pq[mt][j][e];
+                                    double jv = (2.0 * Pq[mt][j][e] - y1[bit * 128] + acc[mt][j][e]) * (1.0 / 6.0);
+                                    double jf = AF[mt][j][e];
+                                    if ((sp >> tile) & 1) {
+                                        const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
+                                        jq += x1q + h * x1v + (dtc ? Vs[3 * NR + r] : 0.0);
+                                        jv += x1v;
+                                        jf += ((mt_ >> bit) & 1) ? TF[r] : 0.0;
                                     }
+                                    __stcs(p, jq);
+                                    __stcs(p + (size_t)n * RSJ, jv);
+                                    __stcs(p + (size_t)2 * n * RSJ, jf);
                                 }
                             }
                         }
