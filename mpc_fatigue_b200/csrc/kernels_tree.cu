@@ -33,14 +33,16 @@ namespace mpcf {
 
 // ------------------------------------------------------------------------------------------------ workspace layout
 struct TreeWs {
-    int n, npat, NE;  // NE planes of 32 doubles per (tile, stage)
-    MPCF_HD static int planes(int n, int npat) { return 5 * npat + 5 * n; }
-    MPCF_HD size_t chunk(long tile, int s) const { return ((size_t)tile * 4 + s) * NE * 32; }
-    // plane indices
-    MPCF_HD int dqkj(int e) const { return e; }
-    MPCF_HD int dqjk(int e) const { return npat + e; }
-    MPCF_HD int dvkj(int e) const { return 2 * npat + e; }
-    MPCF_HD int dvjk(int e) const { return 3 * npat + e; }
+    int n, npat, NE;  // NE doubles per (unit, stage) block, a multiple of 4 (blocks stay 32-byte aligned)
+    MPCF_HD static int planes(int n, int npat) { return (5 * npat + 5 * n + 3) & ~3; }
+    // A (unit, stage) block is contiguous: the chain kernels (CTA = unit) then read whole 32-byte sectors, and the four values of
+    // a pattern entry are adjacent, so the thread-per-unit writer stores one full sector per entry.
+    MPCF_HD size_t at(long u, int s) const { return ((size_t)u * 4 + s) * NE; }
+    // element indices inside a block
+    MPCF_HD int dqkj(int e) const { return 4 * e; }
+    MPCF_HD int dvkj(int e) const { return 4 * e + 1; }
+    MPCF_HD int dqjk(int e) const { return 4 * e + 2; }
+    MPCF_HD int dvjk(int e) const { return 4 * e + 3; }
     MPCF_HD int lf(int e) const { return 4 * npat + e; }
     MPCF_HD int vec(int slot, int i) const { return 5 * npat + slot * n + i; }  // 0 qd_s, 1 qdd_s, 2 fnext_s, 3 q_s, 4 extra_s
 };
@@ -80,22 +82,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_tree_stages(GenericBlob blob, T
         const double cprev = s == 3 ? 1.0 : 0.5;  // c_{s-1}
         const double wt = (s == 0 || s == 3) ? 1.0 / 6.0 : 1.0 / 3.0;
         D::aba(m, xs, xs + n, t, k + n);
-        double *w = ws + W.chunk(u / 32, s) + (u & 31);
-        double *wprev = ws + W.chunk(u / 32, s > 0 ? s - 1 : 0) + (u & 31);
+        double *w = ws + W.at(u, s);
+        double *wprev = ws + W.at(u, s > 0 ? s - 1 : 0);
         for (int i = 0; i < n; ++i) {
             const double qdi = xs[n + i];
             k[i] = qdi;
             k[2 * n + i] = D::fatigue_rhs(m, i, xs[2 * n + i], t[i], qdi);
-            w[W.vec(0, i) * 32] = qdi;
-            w[W.vec(1, i) * 32] = k[n + i];
-            w[W.vec(3, i) * 32] = xs[i];
+            w[W.vec(0, i)] = qdi;
+            w[W.vec(1, i)] = k[n + i];
+            w[W.vec(3, i)] = xs[i];
             const double z = m.fat(i, 0) * h;
             const double gam = s == 0 ? 1.0 + z * (-1.0 + z * (0.5 - 0.25 * z)) : (s == 1 ? 2.0 + z * (-1.0 + 0.5 * z) : (s == 2 ? 2.0 - z : 1.0));
             const double fcoef = gam * (h / 6.0) * 2.0 * m.fat(i, 1) * m.fat(i, 3) * qdi;
             fsum[i] += fcoef;
             gdt[i] += gam * (1.0 / 6.0) * k[2 * n + i];
             qdbar[i] += wt * qdi;
-            if (s > 0) wprev[W.vec(2, i) * 32] = fcoef * cprev;
+            if (s > 0) wprev[W.vec(2, i)] = fcoef * cprev;
         }
         const double a = h * wt, c = h * cs;
         for (int i = 0; i < 3 * n; ++i) {
@@ -104,9 +106,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_tree_stages(GenericBlob blob, T
         }
     }
     for (int i = 0; i < n; ++i) {
-        ws[W.chunk(u / 32, 0) + (size_t)W.vec(4, i) * 32 + (u & 31)] = gdt[i];
-        ws[W.chunk(u / 32, 1) + (size_t)W.vec(4, i) * 32 + (u & 31)] = fsum[i];
-        ws[W.chunk(u / 32, 3) + (size_t)W.vec(4, i) * 32 + (u & 31)] = qdbar[i];
+        ws[W.at(u, 0) + (size_t)W.vec(4, i)] = gdt[i];
+        ws[W.at(u, 1) + (size_t)W.vec(4, i)] = fsum[i];
+        ws[W.at(u, 3) + (size_t)W.vec(4, i)] = qdbar[i];
         if (qn) {
             qn[i * U + u] = xn[i];
             qdn[i * U + u] = xn[n + i];
@@ -117,14 +119,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_tree_stages(GenericBlob blob, T
 
 // ------------------------------------------------------------------------------------------------ T2
 struct TreePackedOut {
-    double *o;  // this lane's element of plane 0 of the (tile, stage) chunk
+    double *o;  // the (unit, stage) block
     TreeWs W;
     MPCF_HD void pair(int, int, int e, double dqkj, double dvkj, double dqjk, double dvjk) const
     {
-        o[(size_t)W.dqkj(e) * 32] = dqkj;
-        o[(size_t)W.dqjk(e) * 32] = dqjk;
-        o[(size_t)W.dvkj(e) * 32] = dvkj;
-        o[(size_t)W.dvjk(e) * 32] = dvjk;
+        double2 *p = reinterpret_cast<double2 *>(o + 4 * (size_t)e);  // one 32-byte sector
+        p[0] = make_double2(dqkj, dvkj);
+        p[1] = make_double2(dqjk, dvjk);
     }
 };
 
@@ -142,12 +143,12 @@ __global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, Tree
     const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= cnt) return;
     const int s = blockIdx.y;
-    double *o = ws + W.chunk(u / 32, s) + (u & 31);
+    double *o = ws + W.at(u, s);
     double q[MAXN], qd[MAXN], qdd[MAXN];
     for (int i = 0; i < n; ++i) {
-        q[i] = o[(size_t)W.vec(3, i) * 32];
-        qd[i] = o[(size_t)W.vec(0, i) * 32];
-        qdd[i] = o[(size_t)W.vec(1, i) * 32];
+        q[i] = o[(size_t)W.vec(3, i)];
+        qd[i] = o[(size_t)W.vec(0, i)];
+        qdd[i] = o[(size_t)W.vec(1, i)];
     }
     TreeRec rec[MAXN];
     TreeComp comp[MAXN];
@@ -158,11 +159,14 @@ __global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, Tree
     TreeDerivs<GenericModel<MAXN>>::factorize(m, Mp);
     // the tensor-core chain kernel multiplies by L^-1 (same packed pattern) instead of solving with L; path / lrow reuse q / qd
     if (want_linv) TreeDerivs<GenericModel<MAXN>>::invert_unit_factor(m, Mp, reinterpret_cast<int *>(q), qd);
-    for (int k = 0; k < n; ++k) {
-        const int e0 = m.rowptr(k), e1 = e0 + m.depth(k);  // e1 = the diagonal entry
-        for (int e = e0; e < e1; ++e) o[(size_t)W.lf(e) * 32] = Mp[e];
-        o[(size_t)W.lf(e1) * 32] = 1.0 / Mp[e1];
+    for (int k = 0; k < n; ++k) {  // the diagonal entries carry 1 / D_k
+        const int e1 = m.rowptr(k) + m.depth(k);
+        Mp[e1] = 1.0 / Mp[e1];
     }
+    double2 *of = reinterpret_cast<double2 *>(o + W.lf(0));  // 16-byte aligned: lf(0) = 4 npat
+    const int npat = W.npat;
+    for (int e = 0; e + 1 < npat; e += 2) of[e >> 1] = make_double2(Mp[e], Mp[e + 1]);
+    if (npat & 1) o[W.lf(npat - 1)] = Mp[npat - 1];
 }
 
 // ------------------------------------------------------------------------------------------------ T3
@@ -184,6 +188,7 @@ struct TreeChainArgs {
     double *scratch;         // [gridDim.x][2][n][128]: fatigue-row sums and P per column (L2-resident, coalesced)
     const double *fat;       // device blob: fat[n][4]
     const int *ints;         // device blob ints: parent n | jtype n | keep n | depth n | rowptr n + 1
+    int dbg;                 // TEMPORARY timing experiments (MPCF_TC_DBG bit mask), 0 in production
     int fence0;              // always 0: `if (a.fence0 > i) continue;` is never taken but cuts the unrolled triangular solves into one
                              // basic block per column (cf. StaticModel::skip); in one block ptxas hoists ~800 loads and spills 6.7 KB
 };
@@ -222,28 +227,28 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain(TreeChainArgs a)
                    sLT = (unsigned)__cvta_generic_to_shared(LT), sV = (unsigned)__cvta_generic_to_shared(V);
     // group A of (unit u, stage s): dID/dq, dID/dqd entries + the four vectors (into vector buffer s & 1); group B: the factor
     auto issue_A = [&](long u, int s) {
-        const double *w = a.ws + W.chunk(u / 32, s) + (u & 31);
+        const double *w = a.ws + W.at(u, s);
         for (int e = t; e < npat; e += 128) {
             const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
-            cp_async8s(sDq + kj, w + (size_t)W.dqkj(e) * 32);
-            cp_async8s(sDv + kj, w + (size_t)W.dvkj(e) * 32);
+            cp_async8s(sDq + kj, w + (size_t)W.dqkj(e));
+            cp_async8s(sDv + kj, w + (size_t)W.dvkj(e));
             if (kj != jk) {
-                cp_async8s(sDq + jk, w + (size_t)W.dqjk(e) * 32);
-                cp_async8s(sDv + jk, w + (size_t)W.dvjk(e) * 32);
+                cp_async8s(sDq + jk, w + (size_t)W.dqjk(e));
+                cp_async8s(sDv + jk, w + (size_t)W.dvjk(e));
             }
         }
         const unsigned vb = sV + (unsigned)((s & 1) * 4 * NR) * 8u;
         for (int i = t; i < n; i += 128) {
-            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, w + (size_t)W.vec(0, i) * 32);
-            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, w + (size_t)W.vec(1, i) * 32);
-            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, w + (size_t)W.vec(2, i) * 32);
-            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, w + (size_t)W.vec(4, i) * 32);
+            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, w + (size_t)W.vec(0, i));
+            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, w + (size_t)W.vec(1, i));
+            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, w + (size_t)W.vec(2, i));
+            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, w + (size_t)W.vec(4, i));
         }
         cp_async_commit();
     };
     auto issue_B = [&](long u, int s) {
-        const double *w = a.ws + W.chunk(u / 32, s) + (u & 31);
-        for (int e = t; e < npat; e += 128) cp_async8s(sLT + okj[e] * 8u, w + (size_t)W.lf(e) * 32);  // L_kj at (row k, col j); diagonal: 1 / D_k
+        const double *w = a.ws + W.at(u, s);
+        for (int e = t; e < npat; e += 128) cp_async8s(sLT + okj[e] * 8u, w + (size_t)W.lf(e));  // L_kj at (row k, col j); diagonal: 1 / D_k
         cp_async_commit();
     };
     double *AF = a.scratch + (size_t)blockIdx.x * 2 * n * 128 + t, *Ps = AF + (size_t)n * 128;
@@ -438,10 +443,12 @@ struct TcLayout {
     static size_t bytes(int npat) { return (size_t)nD * sizeof(double) + (size_t)3 * npat * sizeof(unsigned short); }
 };
 
-template <int NR>
-__global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
+// NJ: n-tiles (8 Jacobian columns each) per warp; 8 / NJ warps per CTA cover the slab's 64 columns
+template <int NR, int NJ>
+__global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
 {
     using Ly = TcLayout<NR>;
+    constexpr int NTH = 256 / NJ;
     constexpr int MT = Ly::MT, RSA = Ly::RSA, RSL = Ly::RSL, XS = Ly::XS, KS1 = Ly::KS1, KS2 = Ly::KS2;
     const TreeWs W = a.W;
     const int n = W.n, npat = W.npat;
@@ -451,11 +458,11 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
     unsigned short *okj = reinterpret_cast<unsigned short *>(sm + Ly::nD), *ojk = okj + npat, *okl = ojk + npat;
     const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
     const int slab = blockIdx.y, nslab = gridDim.y;
-    for (int i = t; i < Ly::oX; i += 128) sm[i] = 0.0;
+    for (int i = t; i < Ly::oX; i += NTH) sm[i] = 0.0;
     __syncthreads();
     {
         const int *parent = a.ints, *depth = a.ints + 3 * n, *rowptr = a.ints + 4 * n;
-        for (int k = t; k < n; k += 128) {
+        for (int k = t; k < n; k += NTH) {
             LI[k * RSL + k] = 1.0;  // unit diagonal of L^-1 (the padding rows stay 0, so the padding rows of every product are 0)
             for (int j = k; j >= 0; j = parent[j]) {
                 const int e = rowptr[k] + depth[j];
@@ -468,57 +475,61 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
     __syncthreads();
     const unsigned sDA = (unsigned)__cvta_generic_to_shared(DA), sLI = (unsigned)__cvta_generic_to_shared(LI), sV = (unsigned)__cvta_generic_to_shared(V);
     auto issue_A = [&](long u, int s) {
-        const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
-        for (int e = t; e < npat; e += 128) {
+        if (a.dbg & 1) { cp_async_commit(); return; }
+        const double *ws = a.ws + W.at(u, s);
+        for (int e = t; e < npat; e += NTH) {
             const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
-            cp_async8s(sDA + kj, ws + (size_t)W.dqkj(e) * 32);
-            cp_async8s(sDA + kj + (unsigned)NR * 8u, ws + (size_t)W.dvkj(e) * 32);
+            cp_async8s(sDA + kj, ws + (size_t)W.dqkj(e));
+            cp_async8s(sDA + kj + (unsigned)NR * 8u, ws + (size_t)W.dvkj(e));
             if (kj != jk) {
-                cp_async8s(sDA + jk, ws + (size_t)W.dqjk(e) * 32);
-                cp_async8s(sDA + jk + (unsigned)NR * 8u, ws + (size_t)W.dvjk(e) * 32);
+                cp_async8s(sDA + jk, ws + (size_t)W.dqjk(e));
+                cp_async8s(sDA + jk + (unsigned)NR * 8u, ws + (size_t)W.dvjk(e));
             }
         }
         const unsigned vb = sV + (unsigned)((s & 1) * 4 * NR) * 8u;
-        for (int i = t; i < n; i += 128) {
-            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, ws + (size_t)W.vec(0, i) * 32);
-            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, ws + (size_t)W.vec(1, i) * 32);
-            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, ws + (size_t)W.vec(2, i) * 32);
-            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, ws + (size_t)W.vec(4, i) * 32);
+        for (int i = t; i < n; i += NTH) {
+            cp_async8s(vb + (unsigned)(0 * NR + i) * 8u, ws + (size_t)W.vec(0, i));
+            cp_async8s(vb + (unsigned)(1 * NR + i) * 8u, ws + (size_t)W.vec(1, i));
+            cp_async8s(vb + (unsigned)(2 * NR + i) * 8u, ws + (size_t)W.vec(2, i));
+            cp_async8s(vb + (unsigned)(3 * NR + i) * 8u, ws + (size_t)W.vec(4, i));
         }
         cp_async_commit();
     };
     auto issue_B = [&](long u, int s) {
-        const double *ws = a.ws + W.chunk(u / 32, s) + (u & 31);
-        for (int e = t; e < npat; e += 128) cp_async8s(sLI + okl[e] * 8u, ws + (size_t)W.lf(e) * 32);
+        if (a.dbg & 1) { cp_async_commit(); return; }
+        const double *ws = a.ws + W.at(u, s);
+        for (int e = t; e < npat; e += NTH) cp_async8s(sLI + okl[e] * 8u, ws + (size_t)W.lf(e));
         cp_async_commit();
     };
     // this thread's fragment elements: rows 8 mt + g, columns cb + 8 j + 2 tq + e (cb = the warp's first column)
-    const int cb = 64 * slab + 16 * w;
+    const int cb = 64 * slab + 8 * NJ * w;
     const long PC = 4 * n + 1;
-    unsigned mq = 0, mv = 0, mt_ = 0;  // bit (mt * 2 + j) * 2 + e: X1[q] = 1, X1[qd] = 1, tau-column unit entry
+    unsigned mq = 0, mv = 0, mt_ = 0;  // bit (mt * NJ + j) * 2 + e: X1[q] = 1, X1[qd] = 1, tau-column unit entry
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int r = 8 * mt + g, c = cb + 8 * j + 2 * tq + e, bit = (mt * 2 + j) * 2 + e;
+                const int r = 8 * mt + g, c = cb + 8 * j + 2 * tq + e, bit = (mt * NJ + j) * 2 + e;
                 if (r < n && c == r) mq |= 1u << bit;
                 if (r < n && c == n + r) mv |= 1u << bit;
                 if (r < n && c == 2 * n + r) mt_ |= 1u << bit;
             }
-    const bool dt0 = cb + 2 * tq == 3 * n, dt1 = cb + 2 * tq + 1 == 3 * n, dt2 = cb + 8 + 2 * tq == 3 * n, dt3 = cb + 8 + 2 * tq + 1 == 3 * n;
-    unsigned sp = 0;  // bit mt * 2 + j: some lane of this warp has a special entry in tile (mt, j) -> warp-uniform
+    bool dtf[NJ][2];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { dtf[j][0] = cb + 8 * j + 2 * tq == 3 * n; dtf[j][1] = cb + 8 * j + 2 * tq + 1 == 3 * n; }
+    unsigned sp = 0;  // bit mt * NJ + j: some lane of this warp has a special entry in tile (mt, j) -> warp-uniform
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int tile = mt * 2 + j;
-            const bool mine = (((mq | mv | mt_) >> (tile * 2)) & 3u) != 0 || (j == 0 ? (dt0 || dt1) : (dt2 || dt3));
+        for (int j = 0; j < NJ; ++j) {
+            const int tile = mt * NJ + j;
+            const bool mine = (((mq | mv | mt_) >> (tile * 2)) & 3u) != 0 || dtf[j][0] || dtf[j][1];
             if (__any_sync(0xffffffffu, mine)) sp |= 1u << tile;
         }
-    auto isdt = [&](int j, int e) { return j == 0 ? (e == 0 ? dt0 : dt1) : (e == 0 ? dt2 : dt3); };
-    const double *Xcol = Xs + 16 * w;  // this warp's 16 columns
+    auto isdt = [&](int j, int e) { return dtf[j][e]; };
+    const double *Xcol = Xs + 8 * NJ * w;  // this warp's columns
     // Units are handed out dynamically (one counter per slab, zeroed by the launcher) instead of strided by CTA: units u .. u + 3
     // share every 32-byte sector of the AoSoA workspace and of the [plane][unit] Jacobian, and only units that are in flight at
     // about the same time meet in L2 (with a static stride the CTAs drift apart: 36 GB of DRAM reads per 32k units instead of 5).
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             const double z = a.fat[4 * t] * h;
             tf = 2.0 * a.fat[4 * t + 1] * a.fat[4 * t + 2] * a.tau[(size_t)t * a.U + u] * h * (1.0 + z * (-0.5 + z * (1.0 / 6.0 - z * (1.0 / 24.0))));
         }
-        double acc[MT][2][2], yv[MT][2][2], Pq[MT][2][2], AF[MT][2][2];
+        double acc[MT][NJ][2], yv[MT][NJ][2], Pq[MT][NJ][2], AF[MT][NJ][2];
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
             cp_async_wait<1>();
@@ -554,7 +565,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)
+                    for (int j = 0; j < NJ; ++j)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int c = cb + 8 * j + 2 * tq + e;
@@ -565,28 +576,34 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+                    for (int j = 0; j < NJ; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
+                if (!(a.dbg & 4)) {
                 const double *ap = DA + g * RSA + tq, *bp = Xcol + tq * XS + g;
-                double af[MT], bf[2], af2[MT], bf2[2];
+                double af[MT], bf[NJ], af2[MT], bf2[NJ];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) af[mt] = ap[8 * mt * RSA];
-                bf[0] = bp[0]; bf[1] = bp[8];
+                for (int j = 0; j < NJ; ++j) bf[j] = bp[8 * j];
 #pragma unroll 1
                 for (int ks = 0; ks < KS1; ks += 2) {  // two k-steps per trip, the next one's fragments loaded ahead of this one's DMMA
                     const double *ap1 = ap + 4 * (ks + 1), *bp1 = bp + 4 * (ks + 1) * XS;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) af2[mt] = ap1[8 * mt * RSA];
-                    bf2[0] = bp1[0]; bf2[1] = bp1[8];
+                    for (int j = 0; j < NJ; ++j) bf2[j] = bp1[8 * j];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) { dmma884(acc[mt][0][0], acc[mt][0][1], af[mt], bf[0]); dmma884(acc[mt][1][0], acc[mt][1][1], af[mt], bf[1]); }
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af[mt], bf[j]);
                     if (ks + 2 < KS1) {
                         const double *ap2 = ap + 4 * (ks + 2), *bp2 = bp + 4 * (ks + 2) * XS;
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) af[mt] = ap2[8 * mt * RSA];
-                        bf[0] = bp2[0]; bf[1] = bp2[8];
+                        for (int j = 0; j < NJ; ++j) bf[j] = bp2[8 * j];
                     }
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) { dmma884(acc[mt][0][0], acc[mt][0][1], af2[mt], bf2[0]); dmma884(acc[mt][1][0], acc[mt][1][1], af2[mt], bf2[1]); }
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af2[mt], bf2[j]);
+                }
                 }
             }
             __syncthreads();
@@ -595,14 +612,14 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             __syncthreads();
             // ---- rhs = E_tau - Z, staged in this warp's (dead) X[q] rows so that the next product reads its B fragments with the same
             //      conflict-free loads as the first one ----
-            double *xw = Xs + 16 * w + 2 * tq;
+            double *xw = Xs + 8 * NJ * w + 2 * tq;
             const double *bq = Xcol + tq * XS + g;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const double r0 = (((mt_ >> ((mt * 2 + j) * 2)) & 1) ? 1.0 : 0.0) - acc[mt][j][0];
-                    const double r1 = (((mt_ >> ((mt * 2 + j) * 2 + 1)) & 1) ? 1.0 : 0.0) - acc[mt][j][1];
+                for (int j = 0; j < NJ; ++j) {
+                    const double r0 = (((mt_ >> ((mt * NJ + j) * 2)) & 1) ? 1.0 : 0.0) - acc[mt][j][0];
+                    const double r1 = (((mt_ >> ((mt * NJ + j) * 2 + 1)) & 1) ? 1.0 : 0.0) - acc[mt][j][1];
                     *reinterpret_cast<double2 *>(xw + (8 * mt + g) * XS + 8 * j) = make_double2(r0, r1);
                     yv[mt][j][0] = 0.0; yv[mt][j][1] = 0.0;
                 }
@@ -610,12 +627,14 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             // ---- T = D^-1 L^-T rhs: A(r, k) = L^-1[k][r], only the tiles with 4 ks + 3 >= 8 mt ----
 #pragma unroll
             for (int ks = 0; ks < KS2; ++ks) {
-                const double b0 = bq[4 * ks * XS], b1 = bq[4 * ks * XS + 8];
+                double bb[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bb[j] = bq[4 * ks * XS + 8 * j];
 #pragma unroll
                 for (int mt = 0; mt <= ks / 2 && mt < MT; ++mt) {
                     const double af = LI[(4 * ks + tq) * RSL + 8 * mt + g];
-                    dmma884(yv[mt][0][0], yv[mt][0][1], af, b0);
-                    dmma884(yv[mt][1][0], yv[mt][1][1], af, b1);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma884(yv[mt][j][0], yv[mt][j][1], af, bb[j]);
                 }
             }
             __syncwarp();
@@ -623,7 +642,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             for (int mt = 0; mt < MT; ++mt) {
                 const double di = DI[8 * mt + g];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     *reinterpret_cast<double2 *>(xw + (8 * mt + g) * XS + 8 * j) = make_double2(yv[mt][j][0] * di, yv[mt][j][1] * di);
                     acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0;
                 }
@@ -632,12 +651,14 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
             // ---- K = L^-1 T: A(r, k) = L^-1[r][k], only the tiles with 4 ks <= 8 mt + 7 ----
 #pragma unroll
             for (int ks = 0; ks < KS2; ++ks) {
-                const double b0 = bq[4 * ks * XS], b1 = bq[4 * ks * XS + 8];
+                double bb[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bb[j] = bq[4 * ks * XS + 8 * j];
 #pragma unroll
                 for (int mt = ks / 2; mt < MT; ++mt) {
                     const double af = LI[(8 * mt + g) * RSL + 4 * ks + tq];
-                    dmma884(acc[mt][0][0], acc[mt][0][1], af, b0);
-                    dmma884(acc[mt][1][0], acc[mt][1][1], af, b1);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af, bb[j]);
                 }
             }
             __syncwarp();
@@ -654,8 +675,8 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                 const int r = 8 * mt + g;
                 const double fn = Vs[2 * NR + r];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int tile = mt * 2 + j;
+                for (int j = 0; j < NJ; ++j) {
+                    const int tile = mt * NJ + j;
                     double2 xvold = make_double2(0.0, 0.0);
                     if (s > 0) xvold = *reinterpret_cast<const double2 *>(xw + (NR + r) * XS + 8 * j);
                     double xqn[2], xvn[2];
@@ -671,7 +692,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                             if (s == 0) {
                                 Pq[mt][j][e] = y;
                                 AF[mt][j][e] = fma(fn, y, dtc ? ex_r : 0.0);
-                                y1[bit * 128] = y;
+                                y1[bit * NTH] = y;
                             } else if (s < 3) {
                                 Pq[mt][j][e] += y;
                                 AF[mt][j][e] = fma(fn, y, AF[mt][j][e] + ((s == 1 && x1v != 0.0) ? ex_r : 0.0));
@@ -688,7 +709,7 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                             if (s == 0) {
                                 Pq[mt][j][e] = y;
                                 AF[mt][j][e] = fn * y;
-                                y1[(tile * 2 + e) * 128] = y;
+                                y1[(tile * 2 + e) * NTH] = y;
                             } else if (s < 3) {
                                 Pq[mt][j][e] += y;
                                 AF[mt][j][e] = fma(fn, y, AF[mt][j][e]);
@@ -703,12 +724,12 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                     }
                 }
             }
-            if (s == 3) {
+            if (s == 3 && !(a.dbg & 2)) {
                 // ---- Jacobian rows, column by column: one pointer per column, stepped by 8 rows per m-tile ----
                 const size_t RSJ = (size_t)PC * a.UJ;  // one Jacobian row (all columns, plane stride UJ)
                 const double h6 = h * (1.0 / 6.0);
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < NJ; ++j)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int c = cb + 8 * j + 2 * tq + e;
@@ -717,10 +738,10 @@ __global__ void __launch_bounds__(128, 2) k_tree_chain_tc(TreeChainArgs a)
                             double *p = a.jac + (size_t)(dtc ? 4 * n : c) * a.UJ + u + (size_t)g * RSJ;
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt, p += 8 * RSJ) {
-                                const int r = 8 * mt + g, tile = mt * 2 + j, bit = tile * 2 + e;
+                                const int r = 8 * mt + g, tile = mt * NJ + j, bit = tile * 2 + e;
                                 if (r < n) {
                                     double jq = h6 * Pq[mt][j][e];
-                                    double jv = (2.0 * Pq[mt][j][e] - y1[bit * 128] + acc[mt][j][e]) * (1.0 / 6.0);
+                                    double jv = (2.0 * Pq[mt][j][e] - y1[bit * NTH] + acc[mt][j][e]) * (1.0 / 6.0);
                                     double jf = AF[mt][j][e];
                                     if ((sp >> tile) & 1) {
                                         const double x1q = ((mq >> bit) & 1) ? 1.0 : 0.0, x1v = ((mv >> bit) & 1) ? 1.0 : 0.0;
@@ -761,6 +782,10 @@ __global__ void __launch_bounds__(256) k_tree_fill_fatigue_cols(int n, long cnt,
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
+#ifndef MPCF_TC_NJ
+#define MPCF_TC_NJ 2
+#endif
+static constexpr int TC_NJ = MPCF_TC_NJ;  // n-tiles per warp of the tensor-core chain kernel: 1 -> 8 warps per CTA, 2 -> 4 warps
 static std::atomic<bool> g_tree_attr[64];
 
 bool tree_jvp_supported(const LaunchModel &m) { return (m.fam == FAM_GENERIC16 || m.fam == FAM_GENERIC64) && m.n <= 40; }
@@ -788,9 +813,9 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tree_chain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_tree_chain_tc<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        e = cudaFuncSetAttribute(k_tree_chain_tc<40, TC_NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_tree_chain_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        e = cudaFuncSetAttribute(k_tree_chain_tc<16, TC_NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
         if (e != cudaSuccess) return e;
         g_tree_attr[dev].store(true, std::memory_order_release);
     }
@@ -815,13 +840,13 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         const char *env = getenv("MPCF_TREE_CHAIN");
         const bool use_tc = !(env && env[0] == 's');
         k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_tc ? 1 : 0);
-        TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
+        TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, getenv("MPCF_TC_DBG") ? atoi(getenv("MPCF_TC_DBG")) : 0, 0};
         if (use_tc) {
             const int nslab = (3 * n + 1 + 63) / 64;
             const long gx_max = (long)nsm * 2 / nslab;
             const unsigned gx = (unsigned)(c < gx_max ? c : gx_max);
             cudaMemsetAsync(scratch, 0, 64, s);  // the per-slab unit counters
-            k_tree_chain_tc<NR><<<dim3(gx, nslab), 128, TcLayout<NR>::bytes(npat), s>>>(a);
+            k_tree_chain_tc<NR, TC_NJ><<<dim3(gx, nslab), 256 / TC_NJ, TcLayout<NR>::bytes(npat), s>>>(a);
             k_tree_fill_fatigue_cols<<<dim3((unsigned)((c + 255) / 256), 3 * n), 256, 0, s>>>(n, c, UJ, a.fat, dt, a.dt_u, a.jac);
             g_launches.fetch_add(1);
         } else {
