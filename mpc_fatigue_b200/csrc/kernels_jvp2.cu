@@ -572,12 +572,8 @@ struct ColumnState {
             __stcs(jac + ((size_t)(ntot + c0 + i) * PC + ocol) * U + u, av[i]);
             __stcs(jac + ((size_t)(2 * ntot + c0 + i) * PC + ocol) * U + u, af[i]);
         }
-        if (!WHOLE && !isdt) {
-            for (int blk = 0; blk < 3; ++blk)
-                for (int i = 0; i < ntot; ++i)
-                    if (i < c0 || i >= c0 + N) __stcs(jac + ((size_t)(blk * ntot + i) * PC + ocol) * U + u, 0.0);
-        }
-        if (isdt) {  // the fatigue columns of this chain in closed form (see kernels_jvp.cu), all 3*ntot rows
+        // (forests: the structural zeros between different chains are written by k_forest_fill_cross, coalesced, once per call)
+        if (isdt) {  // the fatigue columns of this chain in closed form (see kernels_jvp.cu), own rows
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const double z = P.fat[j][0] * h;
@@ -586,8 +582,11 @@ struct ColumnState {
 #pragma unroll
                     for (int r = 0; r < 3 * N; ++r) __stcs(jac + ((size_t)r * PC + 3 * N + j) * U + u, (r == 2 * N + j) ? g : 0.0);
                 } else {
-                    for (int r = 0; r < 3 * ntot; ++r)
-                        __stcs(jac + ((size_t)r * PC + 3 * ntot + c0 + j) * U + u, (r == 2 * ntot + c0 + j) ? g : 0.0);
+#pragma unroll
+                    for (int blk = 0; blk < 3; ++blk)
+#pragma unroll
+                        for (int i = 0; i < N; ++i)
+                            __stcs(jac + ((size_t)(blk * ntot + c0 + i) * PC + 3 * ntot + c0 + j) * U + u, (blk == 2 && i == j) ? g : 0.0);
                 }
             }
         }
@@ -866,6 +865,27 @@ static cudaError_t run_jvp2(const StaticParams<N> &P, long U, long Ucnt, const d
 
 // Forests: the chains are dynamically decoupled, so each runs the single-chain pipeline on its own input planes and writes its
 // block of the whole-model Jacobian (plus the zeros of the cross blocks).
+// Forest Jacobians: every entry between joints of different chains is structurally zero (columns q, qd, tau, f; the dt column
+// is dense).  One coalesced pass: thread = unit, blockIdx.y = Jacobian row, loop over the columns of the other chains.
+template <int L, class V>
+__global__ void __launch_bounds__(256) k_forest_fill_cross(int ntot, long cntv, long UJ, double *jac)
+{
+    const long uv = (long)blockIdx.x * blockDim.x + threadIdx.x;  // unit (V = double) or pair of units (V = double2)
+    if (uv >= cntv) return;
+    const int r = blockIdx.y, rc = (r % ntot) / L, nch = ntot / L;
+    const long PC = 4 * ntot + 1;
+    V zero;
+    memset(&zero, 0, sizeof(V));
+    double *row = jac + (size_t)r * PC * UJ;
+    for (int b = 0; b < 4; ++b)
+        for (int oc = 0; oc < nch; ++oc) {
+            if (oc == rc) continue;
+            double *p = row + (size_t)(b * ntot + oc * L) * UJ;
+#pragma unroll
+            for (int i = 0; i < L; ++i) __stcs(reinterpret_cast<V *>(p + (size_t)i * UJ) + uv, zero);
+        }
+}
+
 template <int L>
 static cudaError_t run_forest(const LaunchModel &m, long U, long Ucnt, const double *q, const double *qd, const double *tau, const double *theat,
                               long UT, const double *f, double dt,
@@ -878,7 +898,12 @@ static cudaError_t run_forest(const LaunchModel &m, long U, long Ucnt, const dou
                                        qdn ? qdn + off : nullptr, fn ? fn + off : nullptr, jac, UJ, ws, Uc, s, m.n, L * c);
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    if (Ucnt % 2 == 0 && UJ % 2 == 0 && (reinterpret_cast<size_t>(jac) & 15) == 0)
+        k_forest_fill_cross<L, double2><<<dim3((unsigned)((Ucnt / 2 + 255) / 256), 3 * m.n), 256, 0, s>>>(m.n, Ucnt / 2, UJ, jac);
+    else
+        k_forest_fill_cross<L, double><<<dim3((unsigned)((Ucnt + 255) / 256), 3 * m.n), 256, 0, s>>>(m.n, Ucnt, UJ, jac);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 bool jvp2_supported(const LaunchModel &m) { return family_chain_len(m.fam) > 0; }

@@ -4,22 +4,26 @@
 // relations (tree_derivs.cuh), and a different chain-rule mapping, because at n = 37 the per-unit products are real matrix
 // products ([37 x 74] . [74 x 112] per stage) and the per-unit matrices do not fit a thread:
 //
-//   T1 k_tree_stages  thread = unit           primal RK4 (ABA), per stage (q_s, qd_s, qdd_s) and the fatigue-row coefficients
-//   T2 k_tree_derivs  thread = (unit, stage)  dID/dq, dID/dqd on the ancestor pattern + M = L^T D L factorised in place
-//                                             (packed: 5 npat values per stage instead of 3 n^2)
-//   T3 k_tree_chain   CTA = unit, thread = Jacobian column (3n + 1 <= 128): per stage
-//                       Z = dID/dq X[q] + dID/dqd X[qd]      rows in registers, matrices broadcast from shared memory
-//                       K = -M^-1 (Z - E_tau)                dense triangular solves with L, D in registers (unrolled)
-//                     X lives in shared memory (column-private), the packed stage data are expanded into dense
-//                     column-major matrices by cp.async scatter copies that run one stage ahead of the arithmetic.
+//   T1 k_tree_stages     thread = unit           primal RK4 (ABA), per stage (q_s, qd_s, qdd_s) and the fatigue-row coefficients
+//   T2 k_tree_derivs     thread = (unit, stage)  dID/dq, dID/dqd on the ancestor pattern, M = L^T D L factorised in place and
+//                                                L inverted in place (packed: 5 npat values per stage instead of 3 n^2)
+//   T3 k_tree_chain_tc   CTA = (unit, slab of 64 Jacobian columns), FP64 tensor cores (mma.sync m8n8k4), per stage
+//                          Z = [dID/dq | dID/dqd] [X[q]; X[qd]],   K = L^-1 D^-1 L^-T (E_tau - Z)   (two triangular products)
+//                        X in shared memory (warp-private columns), accumulators in register fragments; units handed out by an
+//                        atomic counter so that neighbouring units (which share 32-byte sectors of the outputs) stay in L2
+//      k_tree_chain      the DFMA variant (CTA = unit, thread = column, triangular solves with L), MPCF_TREE_CHAIN=scalar:
+//                        kept as an independent cross-check of the tensor-core path
+//      k_tree_fill_fatigue_cols  the closed-form fatigue columns, coalesced
 //
-// Accumulator identities that keep the per-thread register state at ONE array (acc): P and the fatigue-row sums live in a
-// per-CTA scratch in global memory ([row][128 columns]: coalesced, L2-resident) and are updated with fire-and-forget
-// red.global.add, so no stage waits for a load — checked on the host by tests/hostcheck (same formulas as plain loops) and on
-// the GPU against the oracle:
+// Workspace: one contiguous block per (unit, stage); the four values of a pattern entry (dID/dq_kj, dID/dqd_kj, dID/dq_jk,
+// dID/dqd_jk) are adjacent = one 32-byte sector per entry for the thread-per-unit writer, whole sectors for the CTA-per-unit
+// reader (cp.async scatter copies into the dense shared-memory matrices, issued one stage ahead of the arithmetic).
+//
+// Accumulator identities that keep the per-column state small (checked on the host by tests/hostcheck, same formulas as plain
+// loops, and on the GPU against the oracle):
 //   Yv_s = h K_s (+ qdd_s in the dt column),  P = Yv_1 + Yv_2 + Yv_3
 //   d q+ /dz = X1[q] + h X1[qd] + (h/6) P (+ sum_s w_s qd_s in the dt column)
-//   d qd+/dz = X1[qd] + (2 P - Yv_1 + Yv_4) / 6          (X1[qd] - Yv_1/6 is stored after stage 1, the rest added at the end)
+//   d qd+/dz = X1[qd] + (2 P - Yv_1 + Yv_4) / 6
 //   d f+_i/dz = sum_{s<=3} fnext_s[i] Yv_s[i] (+ closed-form terms), fnext_s = c_s gamma_{s+1}(lambda_i h) (h/6) 2 kappa_i cv_i qd_{s+1,i}
 //               with gamma = (1 - z + z^2/2 - z^3/4, 2 - z + z^2/2, 2 - z, 1): the RK4 response of the linear fatigue rows
 //               to a forcing applied at stage s, so the rows need no per-column recursion state.
@@ -188,7 +192,6 @@ struct TreeChainArgs {
     double *scratch;         // [gridDim.x][2][n][128]: fatigue-row sums and P per column (L2-resident, coalesced)
     const double *fat;       // device blob: fat[n][4]
     const int *ints;         // device blob ints: parent n | jtype n | keep n | depth n | rowptr n + 1
-    int dbg;                 // TEMPORARY timing experiments (MPCF_TC_DBG bit mask), 0 in production
     int fence0;              // always 0: `if (a.fence0 > i) continue;` is never taken but cuts the unrolled triangular solves into one
                              // basic block per column (cf. StaticModel::skip); in one block ptxas hoists ~800 loads and spills 6.7 KB
 };
@@ -475,7 +478,6 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
     __syncthreads();
     const unsigned sDA = (unsigned)__cvta_generic_to_shared(DA), sLI = (unsigned)__cvta_generic_to_shared(LI), sV = (unsigned)__cvta_generic_to_shared(V);
     auto issue_A = [&](long u, int s) {
-        if (a.dbg & 1) { cp_async_commit(); return; }
         const double *ws = a.ws + W.at(u, s);
         for (int e = t; e < npat; e += NTH) {
             const unsigned kj = okj[e] * 8u, jk = ojk[e] * 8u;
@@ -496,7 +498,6 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
         cp_async_commit();
     };
     auto issue_B = [&](long u, int s) {
-        if (a.dbg & 1) { cp_async_commit(); return; }
         const double *ws = a.ws + W.at(u, s);
         for (int e = t; e < npat; e += NTH) cp_async8s(sLI + okl[e] * 8u, ws + (size_t)W.lf(e));
         cp_async_commit();
@@ -577,7 +578,6 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) { acc[mt][j][0] = 0.0; acc[mt][j][1] = 0.0; }
-                if (!(a.dbg & 4)) {
                 const double *ap = DA + g * RSA + tq, *bp = Xcol + tq * XS + g;
                 double af[MT], bf[NJ], af2[MT], bf2[NJ];
 #pragma unroll
@@ -603,7 +603,6 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
                     for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) dmma884(acc[mt][j][0], acc[mt][j][1], af2[mt], bf2[j]);
-                }
                 }
             }
             __syncthreads();
@@ -724,7 +723,7 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
                     }
                 }
             }
-            if (s == 3 && !(a.dbg & 2)) {
+            if (s == 3) {
                 // ---- Jacobian rows, column by column: one pointer per column, stepped by 8 rows per m-tile ----
                 const size_t RSJ = (size_t)PC * a.UJ;  // one Jacobian row (all columns, plane stride UJ)
                 const double h6 = h * (1.0 / 6.0);
@@ -840,7 +839,7 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         const char *env = getenv("MPCF_TREE_CHAIN");
         const bool use_tc = !(env && env[0] == 's');
         k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_tc ? 1 : 0);
-        TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, getenv("MPCF_TC_DBG") ? atoi(getenv("MPCF_TC_DBG")) : 0, 0};
+        TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
         if (use_tc) {
             const int nslab = (3 * n + 1 + 63) / 64;
             const long gx_max = (long)nsm * 2 / nslab;
