@@ -95,6 +95,11 @@ def roofline_for(family: str, n: int, units: float, kernel_ms: dict, peak_tflops
                             "fp64_thread_instructions_per_unit": inst_exec,
                             "per_kernel": {k: v["dadd"] + v["dmul"] + v["dfma"] for k, v in wm["kernels"].items()},
                             "what": "executed FP64 instructions / time / DFMA issue rate of the probe (= sm__pipe_fp64_cycles_active)"}
+        tc = wm.get("tensor_core_pipeline")
+        if tc:  # DMMA.8x8x4 = 256 FMA = the work of 8 warp-wide DFMA on the same 64 FMA / clk / SM peak
+            dmma = sum(k.get("dmma_warp_instr", 0) for k in tc["kernels"].values())
+            out["tensor_pipe"] = {"frac": dmma * 256 * units / (total_ms * 1e-3) / (peak_tflops * 1e12 / 2), "dmma_warp_instructions_per_unit": dmma,
+                                  "source": tc["source"], "what": "DMMA.8x8x4 issued (operands padded to 40 x 80 x 64-column slabs) x 256 FMA / time / FMA peak"}
         traffic = wm.get("dram_bytes_per_unit")
         out["traffic"] = traffic * units if traffic else None
         out["traffic_source"] = wm["source"] if traffic else None

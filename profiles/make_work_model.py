@@ -17,8 +17,11 @@ SOURCES = {
     # python profiles/run_kernel.py jvp 4096 1 pilz6x2c 100, launches 9-16: coupled-fatigue pre kernel, both chains, post kernel
     "forest12x6": ("r02/r02_c3_jvp_raw.csv", 409600, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule",
                                                      "couple": "k_couple"}, 1),
-    # python profiles/run_kernel.py jvp 1024 1 humanoid37 40, launches 7-9: the tree pipeline on its first chunk (33,008 units)
-    "generic64": ("r02/r02_c4_tree_raw.csv", 33008, {"tree_stages": "k_tree_stages", "tree_derivs": "k_tree_derivs", "tree_chain": "k_tree_chain"}, 1),
+    # MPCF_TREE_CHAIN=scalar python profiles/run_kernel.py jvp 1024 1 humanoid37 40, launches 7-9: the tree pipeline with the DFMA
+    # chain kernel on its first chunk.  The default (tensor-core) chain kernel runs the same recursion on operands padded to
+    # 40 x 80 x 64-column slabs; its padding is not work, so the algorithmic count of C4 is the unpadded DFMA variant's
+    # (units of the chunk: grid of k_tree_stages x 128 threads).  The tensor-core capture itself: r02/r02_c4_tc_raw.csv.
+    "generic64": ("r02/r02_c4_tree_raw.csv", None, {"tree_stages": "k_tree_stages", "tree_derivs": "k_tree_derivs", "tree_chain": "k_tree_chain"}, 1),
 }
 
 
@@ -39,6 +42,9 @@ def main():
         hdr, data = rows[0], rows[2:]
         ix = {h: i for i, h in enumerate(hdr)}
         kernels, dram = {}, 0.0
+        if units is None:  # thread-per-unit first kernel: units = its grid x block (exact up to the last block's padding)
+            r0 = next(r for r in data if re.search(next(iter(labels.values())), r[ix["Kernel Name"]]))
+            units = int(num(r0[ix["launch__grid_size"]]) * num(r0[ix["launch__block_size"]]))
         for r in data:
             name = r[ix["Kernel Name"]]
             label = next((lb for lb, rx in labels.items() if re.search(rx, name)), None)
@@ -58,6 +64,27 @@ def main():
             for op in ("dadd", "dmul", "dfma"):
                 k[op] = round(k[op] / reps * mult)
         out[fam] = {"kernels": kernels, "dram_bytes_per_unit": round(dram / reps), "source": "profiles/" + path, "units_per_launch": units}
+    # the default chain kernel of the tree pipeline runs on the FP64 tensor cores: DMMA.8x8x4 warp instructions per unit from
+    # the tensor sub-pipe's active cycles (16 per instruction and SM sub-partition), for the tensor-pipe utilisation in bench.py
+    tc = os.path.join(HERE, "r02/r02_c4_tc_raw.csv")
+    if os.path.exists(tc) and "generic64" in out:
+        rows = list(csv.reader(open(tc)))
+        hdr, data = rows[0], rows[2:]
+        ix = {h: i for i, h in enumerate(hdr)}
+        r0 = next(r for r in data if "k_tree_stages" in r[ix["Kernel Name"]])
+        units = int(num(r0[ix["launch__grid_size"]]) * num(r0[ix["launch__block_size"]]))
+        info = {"source": "profiles/r02/r02_c4_tc_raw.csv", "units_per_launch": units, "kernels": {}}
+        for r in data:
+            name = r[ix["Kernel Name"]].split("(")[0]
+            smsp = 4 * num(r[ix["device__attribute_multiprocessor_count"]])
+            dmma = num(r[ix["smsp__pipe_tensor_subpipe_dmma_cycles_active.avg"]]) * smsp / 16.0 / units
+            cyc = num(r[ix["smsp__cycles_elapsed.avg"]])
+            k = {"dmma_warp_instr": round(dmma), "ms": num(r[ix["gpu__time_duration.sum"]]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
+                rows[1][ix["gpu__time_duration.sum"]], 1.0)}
+            for op in ("dadd", "dmul", "dfma"):
+                k[op] = round(num(r[ix["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op]]) * cyc / units)
+            info["kernels"][name] = k
+        out["generic64"]["tensor_core_pipeline"] = info
     with open(os.path.join(HERE, "work_model.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)
     for fam, v in out.items():

@@ -17,7 +17,9 @@ TOL = 1e-9
 MODELS = {
     "humanoid37": lambda: Model.synthetic("humanoid", 37, seed=7, armature=1e-2),
     "chain9": lambda: Model.synthetic("chain", 9, seed=4, armature=1e-2),
-    "chain40": lambda: Model.synthetic("chain", 40, seed=6, armature=1e-2),
+    "chain40": lambda: Model.synthetic("chain", 40, seed=6, armature=1e-2),      # two full 64-column slabs (121 columns)
+    "humanoid21": lambda: Model.synthetic("humanoid", 21, seed=3, armature=1e-2),  # one slab of the 40-row kernel (64 columns)
+    "humanoid25": lambda: Model.synthetic("humanoid", 25, seed=5, armature=1e-2),  # 76 columns: a second, mostly empty slab
     "mixed": lambda: Model.from_urdf(open(os.path.join(ROOT, "tests", "golden", "mixed_joints.urdf")).read(), armature=1e-3),
 }
 
