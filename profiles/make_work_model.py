@@ -73,11 +73,12 @@ def main():
         ix = {h: i for i, h in enumerate(hdr)}
         r0 = next(r for r in data if "k_tree_stages" in r[ix["Kernel Name"]])
         units = int(num(r0[ix["launch__grid_size"]]) * num(r0[ix["launch__block_size"]]))
+        dcol = next(h for h in hdr if h.endswith("smsp__pipe_tensor_subpipe_dmma_cycles_active.avg"))
         info = {"source": "profiles/r02/r02_c4_tc_raw.csv", "units_per_launch": units, "kernels": {}}
         for r in data:
             name = r[ix["Kernel Name"]].split("(")[0]
             smsp = 4 * num(r[ix["device__attribute_multiprocessor_count"]])
-            dmma = num(r[ix["smsp__pipe_tensor_subpipe_dmma_cycles_active.avg"]]) * smsp / 16.0 / units
+            dmma = num(r[ix[dcol]]) * smsp / 16.0 / units
             cyc = num(r[ix["smsp__cycles_elapsed.avg"]])
             k = {"dmma_warp_instr": round(dmma), "ms": num(r[ix["gpu__time_duration.sum"]]) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(
                 rows[1][ix["gpu__time_duration.sum"]], 1.0)}
