@@ -5,8 +5,9 @@
 // products ([37 x 74] . [74 x 112] per stage) and the per-unit matrices do not fit a thread:
 //
 //   T1 k_tree_stages     thread = unit           primal RK4 (ABA), per stage (q_s, qd_s, qdd_s) and the fatigue-row coefficients
-//   T2 k_tree_derivs     thread = (unit, stage)  dID/dq, dID/dqd on the ancestor pattern, M = L^T D L factorised in place and
-//                                                L inverted in place (packed: 5 npat values per stage instead of 3 n^2)
+//   T2 k_tree_derivs     thread = (unit, stage)  dID/dq, dID/dqd and M on the ancestor pattern (packed: 5 npat values per stage
+//                                                instead of 3 n^2)
+//      k_tree_factor     warp = (unit, stage)    M = L^T D L and L^-1 in place, in shared memory
 //   T3 k_tree_chain_tc   CTA = (unit, slab of 64 Jacobian columns), FP64 tensor cores (mma.sync m8n8k4), per stage
 //                          Z = [dID/dq | dID/dqd] [X[q]; X[qd]],   K = L^-1 D^-1 L^-T (E_tau - Z)   (two triangular products)
 //                        X in shared memory (warp-private columns), accumulators in register fragments; units handed out by an
@@ -134,7 +135,7 @@ struct TreePackedOut {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws, int want_linv)
+__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws)
 {
     extern __shared__ double smem[];
     const int n = blob.n;
@@ -156,21 +157,110 @@ __global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, Tree
     }
     TreeRec rec[MAXN];
     TreeComp comp[MAXN];
-    double Mp[MAXN * (MAXN + 1) / 2];
     TreePackedOut out{o, W};
     TreeDerivs<GenericModel<MAXN>>::forward(m, q, qd, qdd, rec);
-    TreeDerivs<GenericModel<MAXN>>::backward(m, rec, comp, Mp, out);
-    TreeDerivs<GenericModel<MAXN>>::factorize(m, Mp);
-    // the tensor-core chain kernel multiplies by L^-1 (same packed pattern) instead of solving with L; path / lrow reuse q / qd
-    if (want_linv) TreeDerivs<GenericModel<MAXN>>::invert_unit_factor(m, Mp, reinterpret_cast<int *>(q), qd);
-    for (int k = 0; k < n; ++k) {  // the diagonal entries carry 1 / D_k
-        const int e1 = m.rowptr(k) + m.depth(k);
-        Mp[e1] = 1.0 / Mp[e1];
+    // M goes straight to its place in the (unit, stage) block (the thread's own contiguous run of sectors): k_tree_factor
+    // factorises and inverts it there, a warp per block, in shared memory
+    TreeDerivs<GenericModel<MAXN>>::backward(m, rec, comp, o + W.lf(0), out);
+}
+
+// ------------------------------------------------------------------------------------------------ T2b
+// M = L^T D L on the packed ancestor pattern, then L^-1 (same pattern), one WARP per (unit, stage), all in shared memory.  The
+// thread-per-unit versions (tree_derivs.cuh: factorize, invert_unit_factor — same arithmetic in the same order, kept for the
+// host check) were a third of k_tree_derivs' local-memory traffic (k_tree_derivs 4.3 -> 3.3 ms per 33 k units without them; a
+// thread-per-unit kernel with the matrix in shared memory fits only two warps per SM and takes 3.8 ms, this one 1.1 ms).  Both
+// loops expose their parallelism through tables built once per (persistent) block:
+//   factorisation, step k = n-1 .. 0: the updates M_ij -= (M_ki / D_k) M_kj over all pairs j <= i of ancestors of k are
+//     independent (they read row k, which the step only rescales afterwards): lanes over the dk (dk + 1) / 2 pairs;
+//   inversion: Linv_id = -L_id - sum_{d < e < depth(i)} L_ie Linv_{anc_e(i), d} needs only entries with a smaller ancestor distance
+//     depth(i) - d, so all entries of one distance are independent: lanes over the entries, bucketed by distance.
+// Output in place: strictly-lower entries L^-1 (or L when want_linv == 0), diagonal 1 / D_k (NaN for a non-positive pivot).
+template <int MAXN>
+__global__ void __launch_bounds__(256) k_tree_factor(GenericBlob blob, TreeWs W, long cnt, double *ws, int want_linv)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    const int n = blob.n, npat = W.npat, t = threadIdx.x, w = t >> 5, l = t & 31;
+    double *Mw = reinterpret_cast<double *>(fsm) + (size_t)w * 2 * npat, *Lw = Mw + npat;
+    unsigned short *arow = reinterpret_cast<unsigned short *>(reinterpret_cast<double *>(fsm) + (size_t)8 * 2 * npat);  // [n][n]: row offset of the ancestor of k at depth a
+    unsigned short *order = arow + n * n, *bstart = order + npat, *rowp = bstart + (n + 2);
+    unsigned char *tri = reinterpret_cast<unsigned char *>(rowp + (n + 1));  // [n (n + 1) / 2][2]
+    unsigned char *erow = tri + n * (n + 1), *edep = erow + npat, *dep = edep + npat;
+    __shared__ int s_maxd;
+    {
+        const int *parent = blob.ints, *depth = blob.ints + 3 * n, *rowptr = blob.ints + 4 * n;
+        for (int k = t; k <= n; k += 256) rowp[k] = (unsigned short)rowptr[k];
+        for (int k = t; k < n; k += 256) {
+            dep[k] = (unsigned char)depth[k];
+            for (int j = k; j >= 0; j = parent[j]) {
+                arow[k * n + depth[j]] = (unsigned short)rowptr[j];
+                const int e = rowptr[k] + depth[j];
+                erow[e] = (unsigned char)k;
+                edep[e] = (unsigned char)depth[j];
+            }
+        }
+        for (int idx = t; idx < n * (n + 1) / 2; idx += 256) {
+            int a = 0;
+            while ((a + 1) * (a + 2) / 2 <= idx) ++a;
+            tri[2 * idx] = (unsigned char)a;
+            tri[2 * idx + 1] = (unsigned char)(idx - a * (a + 1) / 2);
+        }
+        __syncthreads();
+        if (t == 0) {  // strictly-lower entries bucketed by ancestor distance (counting sort, once per block)
+            int md = 0;
+            for (int k = 0; k < n; ++k) md = depth[k] > md ? depth[k] : md;
+            s_maxd = md;
+            for (int d = 0; d <= n + 1; ++d) bstart[d] = 0;
+            for (int e = 0; e < npat; ++e) {
+                const int dist = dep[erow[e]] - edep[e];
+                if (dist > 0) ++bstart[dist + 1];
+            }
+            for (int d = 1; d <= n + 1; ++d) bstart[d] = (unsigned short)(bstart[d] + bstart[d - 1]);
+            for (int e = 0; e < npat; ++e) {
+                const int dist = dep[erow[e]] - edep[e];
+                if (dist > 0) order[bstart[dist]++] = (unsigned short)e;
+            }
+            for (int d = n + 1; d > 0; --d) bstart[d] = bstart[d - 1];  // bucket d = [bstart[d], bstart[d + 1])
+            bstart[0] = 0;
+        }
+        __syncthreads();
     }
-    double2 *of = reinterpret_cast<double2 *>(o + W.lf(0));  // 16-byte aligned: lf(0) = 4 npat
-    const int npat = W.npat;
-    for (int e = 0; e + 1 < npat; e += 2) of[e >> 1] = make_double2(Mp[e], Mp[e + 1]);
-    if (npat & 1) o[W.lf(npat - 1)] = Mp[npat - 1];
+    const int maxd = s_maxd;
+    const double nanv = nan_value();
+    for (long item = (long)blockIdx.x * 8 + w; item < cnt * 4; item += (long)gridDim.x * 8) {
+        double *o = ws + W.at(item >> 2, (int)(item & 3)) + W.lf(0);
+        for (int e = l; e < npat; e += 32) Mw[e] = o[e];
+        __syncwarp();
+        for (int k = n - 1; k >= 0; --k) {
+            const int rk = rowp[k], dk = dep[k];
+            double d = Mw[rk + dk];
+            if (!(d > 0.0)) d = nanv;
+            const double dinv = 1.0 / d;
+            for (int idx = l; idx < dk * (dk + 1) / 2; idx += 32) {
+                const int a = tri[2 * idx], b = tri[2 * idx + 1];  // b <= a < dk
+                Mw[arow[k * n + a] + b] -= (Mw[rk + a] * dinv) * Mw[rk + b];
+            }
+            __syncwarp();
+            for (int a = l; a < dk; a += 32) Mw[rk + a] *= dinv;
+            if (l == 0) Mw[rk + dk] = d;
+            __syncwarp();
+        }
+        if (want_linv) {
+            for (int dist = 1; dist <= maxd; ++dist) {
+                for (int i = bstart[dist] + l; i < bstart[dist + 1]; i += 32) {
+                    const int e = order[i], r = erow[e], d = edep[e], rr = rowp[r], dr = dep[r];
+                    double sum = -Mw[rr + d];
+                    for (int ee = d + 1; ee < dr; ++ee) sum -= Mw[rr + ee] * Lw[arow[r * n + ee] + d];
+                    Lw[rr + d] = sum;
+                }
+                __syncwarp();
+            }
+        }
+        for (int e = l; e < npat; e += 32) {
+            const bool diag = edep[e] == dep[erow[e]];
+            o[e] = diag ? 1.0 / Mw[e] : (want_linv ? Lw[e] : Mw[e]);
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ T3
@@ -789,6 +879,10 @@ static std::atomic<bool> g_tree_attr[64];
 
 bool tree_jvp_supported(const LaunchModel &m) { return (m.fam == FAM_GENERIC16 || m.fam == FAM_GENERIC64) && m.n <= 40; }
 
+static size_t tree_factor_smem(int n, int npat)
+{
+    return (size_t)8 * 2 * npat * sizeof(double) + ((size_t)n * n + npat + (n + 2) + (n + 1)) * sizeof(unsigned short) + (size_t)n * (n + 1) + 2 * npat + n + 16;
+}
 static size_t tree_chain_smem(int n, int NR, int npat)
 {
     const int NC = 3 * n + 1, XS = (NC + 15) & ~15;
@@ -811,6 +905,10 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         cudaError_t e = cudaFuncSetAttribute(k_tree_chain<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tree_chain<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tree_factor<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tree_factor<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tree_chain_tc<40, TC_NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e != cudaSuccess) return e;
@@ -838,7 +936,13 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
         // recursion with triangular solves instead of the products with L^-1)
         const char *env = getenv("MPCF_TREE_CHAIN");
         const bool use_tc = !(env && env[0] == 's');
-        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws, use_tc ? 1 : 0);
+        k_tree_derivs<MAXN><<<dim3(gb, 4), kThreads, smem12, s>>>(m.blob, W, c, ws);
+        {
+            const long blocks = (c * 4 + 7) / 8;
+            const long cap = (long)nsm * 4;
+            k_tree_factor<MAXN><<<(unsigned)(blocks < cap ? blocks : cap), 256, tree_factor_smem(n, npat), s>>>(m.blob, W, c, ws, use_tc ? 1 : 0);
+            g_launches.fetch_add(1);
+        }
         TreeChainArgs a{W, U, UJ, c, tau + u0, dt_u ? dt_u + u0 : nullptr, dt, ws, jac + u0, scratch, m.blob.dbl + 23 * n, m.blob.ints, 0};
         if (use_tc) {
             const int nslab = (3 * n + 1 + 63) / 64;
