@@ -17,11 +17,11 @@ SOURCES = {
     # python profiles/run_kernel.py jvp 4096 1 pilz6x2c 100, launches 9-16: coupled-fatigue pre kernel, both chains, post kernel
     "forest12x6": ("r02/r02_c3_jvp_raw.csv", 409600, {"step_stages": "k_step_stages", "stage_derivs": "k_stage_derivs", "chain_rule": "k_chain_rule",
                                                      "couple": "k_couple"}, 1),
-    # MPCF_TREE_CHAIN=scalar python profiles/run_kernel.py jvp 1024 1 humanoid37 40, launches 7-9: the tree pipeline with the DFMA
+    # MPCF_TREE_CHAIN=scalar python profiles/run_kernel.py jvp 1024 1 humanoid37 40, launches 9-12: the tree pipeline with the DFMA
     # chain kernel on its first chunk.  The default (tensor-core) chain kernel runs the same recursion on operands padded to
     # 40 x 80 x 64-column slabs; its padding is not work, so the algorithmic count of C4 is the unpadded DFMA variant's
     # (units of the chunk: grid of k_tree_stages x 128 threads).  The tensor-core capture itself: r02/r02_c4_tc_raw.csv.
-    "generic64": ("r02/r02_c4_tree_raw.csv", None, {"tree_stages": "k_tree_stages", "tree_derivs": "k_tree_derivs", "tree_chain": "k_tree_chain"}, 1),
+    "generic64": ("r02/r02_c4_tree_raw.csv", None, {"tree_stages": "k_tree_stages", "tree_derivs": "k_tree_derivs", "tree_factor": "k_tree_factor", "tree_chain": "k_tree_chain"}, 1),
 }
 
 

@@ -15,10 +15,10 @@ ncu --set full --clock-control none --import-source on -k regex:"k_step_stages|k
 python profiles/run_kernel.py jvp 4096 1 pilz6x2c 100 > $O/c3_plain.txt 2>&1 &&
 ncu --set full --clock-control none -k regex:"k_step_stages|k_stage_derivs|k_chain_rule|k_couple|k_forest_fill" -s 9 -c 9 -o $O/r02_c3_jvp python profiles/run_kernel.py jvp 4096 1 pilz6x2c 100 > $O/c3_ncu.log 2>&1
 python profiles/run_kernel.py jvp 1024 2 humanoid37 40 > $O/c4_plain.txt 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_tree" -s 8 -c 4 -o $O/r02_c4_tc python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/c4_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_tree" -s 10 -c 5 -o $O/r02_c4_tc python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/c4_ncu.log 2>&1
 # the DFMA variant of the chain kernel (no padding): its executed-FLOP count is the work model of C4
 MPCF_TREE_CHAIN=scalar python profiles/run_kernel.py jvp 1024 2 humanoid37 40 > $O/c4_scalar_plain.txt 2>&1 &&
-MPCF_TREE_CHAIN=scalar ncu --set full --clock-control none -k regex:"k_tree" -s 6 -c 3 -o $O/r02_c4_tree python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/c4s_ncu.log 2>&1
+MPCF_TREE_CHAIN=scalar ncu --set full --clock-control none -k regex:"k_tree" -s 8 -c 4 -o $O/r02_c4_tree python profiles/run_kernel.py jvp 1024 1 humanoid37 40 > $O/c4s_ncu.log 2>&1
 for r in r02_c2_jvp r02_c3_jvp r02_c4_tc r02_c4_tree; do
   [ -f $O/$r.ncu-rep ] && ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null
 done
