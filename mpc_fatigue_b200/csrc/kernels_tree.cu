@@ -644,12 +644,15 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
         double acc[MT][NJ][2], yv[MT][NJ][2], Pq[MT][NJ][2], AF[MT][NJ][2];
 #pragma unroll 1
         for (int s = 0; s < 4; ++s) {
-            cp_async_wait<1>();
+            // copy groups in flight here: this stage's matrices (A) and, at stage 1 only, its factor (B, issued behind the previous
+            // unit's last product); the factor of stages 2-4 is issued right below, once every warp has left the previous update
+            if (s == 0) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncthreads();
             if (s == 3) un = (long)s_unit[par ^ 1];
             const bool more = s < 3 || un < a.cnt;
             const long u2 = s < 3 ? u : un;
             const int s2 = s < 3 ? s + 1 : 0;
+            if (s > 0) issue_B(u, s);
             if (s == 0 && t < n) TF[t] = tf;  // every warp has left the previous unit's epilogue; read after many barriers
             // ---- Z ----
             if (s == 0) {  // X1 = unit columns: Z is a column of dID/dq (q columns), of dID/dqd (qd columns) or 0
@@ -751,8 +754,10 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
                 }
             }
             __syncwarp();
-            __syncthreads();
-            if (more) issue_B(u2, s2); else cp_async_commit();
+            if (s == 3) {  // the next unit's first factor: its stage 1 has no product to hide the copy behind
+                __syncthreads();
+                if (more) issue_B(u2, 0); else cp_async_commit();
+            }
             // ---- update: Yv, accumulators, next stage's X (warp-private columns).  Per 8 x 8 tile one warp-uniform branch: only the
             //      few tiles that hold a unit entry of X1, a tau-column unit entry or the dt column take the general form ----
             const double cs = s < 2 ? 0.5 : (s == 2 ? 1.0 : 0.0);
