@@ -34,6 +34,13 @@
 #include "launch.cuh"
 #include "tree_derivs.cuh"
 
+#ifndef MPCF_T1_BLOCKS
+#define MPCF_T1_BLOCKS 2
+#endif
+#ifndef MPCF_T2_BLOCKS
+#define MPCF_T2_BLOCKS 3
+#endif
+
 namespace mpcf {
 
 // ------------------------------------------------------------------------------------------------ workspace layout
@@ -55,7 +62,7 @@ size_t tree_ws_doubles_per_unit(int n, int npat) { return (size_t)4 * TreeWs::pl
 
 // ------------------------------------------------------------------------------------------------ T1
 template <int MAXN>
-__global__ void __launch_bounds__(kThreads, 3) k_tree_stages(GenericBlob blob, TreeWs W, long U, long cnt, const double *q, const double *qd,
+__global__ void __launch_bounds__(kThreads, MPCF_T1_BLOCKS) k_tree_stages(GenericBlob blob, TreeWs W, long U, long cnt, const double *q, const double *qd,
                                                             const double *tau, const double *f, double dt, const double *dt_u, double *qn,
                                                             double *qdn, double *fn, double *ws)
 {
@@ -135,7 +142,7 @@ struct TreePackedOut {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(kThreads) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws)
+__global__ void __launch_bounds__(kThreads, MPCF_T2_BLOCKS) k_tree_derivs(GenericBlob blob, TreeWs W, long cnt, double *ws)
 {
     extern __shared__ double smem[];
     const int n = blob.n;
