@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(256 / NJ, 2) k_tree_chain_tc(TreeChainArgs a)
     double *DA = sm + Ly::oDA, *LI = sm + Ly::oLI, *DI = sm + Ly::oDI, *V = sm + Ly::oV, *TF = sm + Ly::oTF, *Xs = sm + Ly::oX, *Y1 = sm + Ly::oY1;
     unsigned short *okj = reinterpret_cast<unsigned short *>(sm + Ly::nD), *ojk = okj + npat, *okl = ojk + npat;
     const int t = threadIdx.x, w = t >> 5, l = t & 31, g = l >> 2, tq = l & 3;
-    const int slab = blockIdx.y, nslab = gridDim.y;
+    const int slab = blockIdx.y;
     for (int i = t; i < Ly::oX; i += NTH) sm[i] = 0.0;
     __syncthreads();
     {
