@@ -937,6 +937,10 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
     long Uc = (long)((ws_bytes - scratch_bytes) / per_unit);
     Uc -= Uc % 32;
     if (Uc < 32) return cudaErrorInvalidValue;
+    // whole waves of the derivative kernel (thread = (unit, stage), three 128-thread blocks per SM: 96 units per SM and wave):
+    // a chunk of 2.34 waves leaves its last wave a third full (measured: 28,416-unit chunks +2.5 % over 32,768 on 148 SMs)
+    const long wave = (long)nsm * 96;
+    if (Uc > wave) Uc -= Uc % wave;
     double *scratch = ws + (size_t)Uc * tree_ws_doubles_per_unit(n, npat);
     const size_t smem12 = blob_smem_bytes(n);
     for (long u0 = 0; u0 < cnt; u0 += Uc) {
@@ -975,8 +979,12 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
 
 size_t tree_jvp_workspace_bytes(int n, int npat, long U)
 {
-    long units = U < (1L << 15) ? U : (1L << 15);  // chunks of at most 32768 units (1.9 GB for the 37-joint tree)
+    long units = U < (1L << 15) ? U : (1L << 15);  // chunks of at most 32768 units (1.9 GB for the 37-joint tree) ...
     units = (units + 31) / 32 * 32;
+    int dev = 0, nsm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const long wave = (long)nsm * 96;  // ... cut to whole waves of the derivative kernel (see run_tree)
+    if (units > wave) units -= units % wave;
     const size_t scratch = (size_t)148 * 4 * 2 * 40 * 128 * sizeof(double);  // generous: up to 2x the CTAs of a 148-SM part
     return (size_t)units * tree_ws_doubles_per_unit(n, npat) * sizeof(double) + scratch;
 }
