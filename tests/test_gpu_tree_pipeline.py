@@ -20,6 +20,8 @@ MODELS = {
     "chain40": lambda: Model.synthetic("chain", 40, seed=6, armature=1e-2),      # two full 64-column slabs (121 columns)
     "humanoid21": lambda: Model.synthetic("humanoid", 21, seed=3, armature=1e-2),  # one slab of the 40-row kernel (64 columns)
     "humanoid25": lambda: Model.synthetic("humanoid", 25, seed=5, armature=1e-2),  # 76 columns: a second, mostly empty slab
+    "two_roots10": lambda: Model.synthetic("dual_arm", 10, seed=3, armature=1e-2),  # two trees in one model (16-row kernel)
+    "two_roots18": lambda: Model.synthetic("dual_arm", 18, seed=3, armature=1e-2),  # the same through the 40-row kernel
     "mixed": lambda: Model.from_urdf(open(os.path.join(ROOT, "tests", "golden", "mixed_joints.urdf")).read(), armature=1e-3),
 }
 
