@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, MPCF_T2_BLOCKS) k_tree_derivs(Generi
     TreeRec rec[MAXN];
     TreeComp comp[MAXN];
     TreePackedOut out{o, W};
-    TreeDerivs<GenericModel<MAXN>>::forward(m, q, qd, qdd, rec);
+    TreeDerivs<GenericModel<MAXN>>::forward(m, q, qd, qdd, rec, comp);
     // M goes straight to its place in the (unit, stage) block (the thread's own contiguous run of sectors): k_tree_factor
     // factorises and inverts it there, a warp per block, in shared memory
     TreeDerivs<GenericModel<MAXN>>::backward(m, rec, comp, o + W.lf(0), out);

@@ -38,7 +38,9 @@ template <class MP>
 struct TreeDerivs {
     static constexpr int MAXN = MP::MAXN;
 
-    static MPCF_HD void forward(const MP &m, const double *q, const double *qd, const double *qdd, TreeRec *rec)
+    // comp[i] leaves this pass holding link i's OWN world-frame inertia, momentum, force and B-matrix: the backward pass adds the
+    // children's composites to it (no zero-initialisation pass, and the backward pass never reads R, o, v, a again).
+    static MPCF_HD void forward(const MP &m, const double *q, const double *qd, const double *qdd, TreeRec *rec, TreeComp *comp)
     {
         const int n = m.n();
         for (int i = 0; i < n; ++i) {
@@ -84,6 +86,8 @@ struct TreeDerivs {
                 r.v[k] = vp[k] + r.K.S[k] * qd[i];
                 r.a[k] = ap[k] + r.K.S[k] * qdd[i] - r.K.xi[k] * qd[i];
             }
+            TreeComp &own = comp[i];
+            FdDerivs<MP, 1>::link_world(m, i, r.R, r.o, r.v, r.a, own.I, own.H, own.F, own.B);
         }
     }
 
@@ -94,23 +98,9 @@ struct TreeDerivs {
     static MPCF_HD void backward(const MP &m, const TreeRec *rec, TreeComp *comp, double *Mp, Out &out)
     {
         const int n = m.n();
-        for (int i = 0; i < n; ++i) {
-            TreeComp &c = comp[i];
-            c.I.m = 0.0;
-            for (int k = 0; k < 3; ++k) c.I.h[k] = 0.0;
-            for (int k = 0; k < 6; ++k) { c.I.Io[k] = 0.0; c.H[k] = 0.0; c.F[k] = 0.0; c.B[k] = 0.0; }
-        }
         for (int k = n - 1; k >= 0; --k) {
             const TreeRec &r = rec[k];
-            TreeComp &c = comp[k];
-            {
-                RigidInertiaW Ik;
-                double Hk[6], Fk[6], Bk[6];
-                FdDerivs<MP, 1>::link_world(m, k, r.R, r.o, r.v, r.a, Ik, Hk, Fk, Bk);
-                c.I.m += Ik.m;
-                for (int e = 0; e < 3; ++e) c.I.h[e] += Ik.h[e];
-                for (int e = 0; e < 6; ++e) { c.I.Io[e] += Ik.Io[e]; c.H[e] += Hk[e]; c.F[e] += Fk[e]; c.B[e] += Bk[e]; }
-            }
+            TreeComp &c = comp[k];  // own values (forward pass) + the composites of the children already visited
             double rk[6], sk[3], gk[6], gvk[6];
             FdDerivs<MP, 1>::pair_vectors(c.I, c.H, c.F, c.B, r.K, rk, sk, gk, gvk);
             const int row = m.rowptr(k);

@@ -66,7 +66,7 @@ extern "C" int hc_tree_derivs(int n, const int *parent, const int *jtype, const 
     std::memset(M, 0, sizeof(double) * n * n);
     std::memset(Lfac, 0, sizeof(double) * n * n);
     DenseOut out{n, Dq, Dv};
-    TreeDerivs<HostTree>::forward(m, q, qd, qdd, rec.data());
+    TreeDerivs<HostTree>::forward(m, q, qd, qdd, rec.data(), comp.data());
     TreeDerivs<HostTree>::backward(m, rec.data(), comp.data(), Mp.data(), out);
     for (int k = 0; k < n; ++k)
         for (int j = k; j >= 0; j = parent[j]) M[k * n + j] = M[j * n + k] = Mp[tp.rowptr[k] + tp.depth[j]];
@@ -94,7 +94,7 @@ extern "C" int hc_tree_linv(int n, const int *parent, const int *jtype, const do
     std::vector<double> Mp(tp.rowptr[n]), Dq(n * n), Dv(n * n), lrow(n);
     std::vector<int> path(n);
     DenseOut out{n, Dq.data(), Dv.data()};
-    TreeDerivs<HostTree>::forward(m, q, qd, qdd, rec.data());
+    TreeDerivs<HostTree>::forward(m, q, qd, qdd, rec.data(), comp.data());
     TreeDerivs<HostTree>::backward(m, rec.data(), comp.data(), Mp.data(), out);
     const bool ok = TreeDerivs<HostTree>::factorize(m, Mp.data());
     TreeDerivs<HostTree>::invert_unit_factor(m, Mp.data(), path.data(), lrow.data());
