@@ -40,9 +40,12 @@ struct TreeDerivs {
 
     // comp[i] leaves this pass holding link i's OWN world-frame inertia, momentum, force and B-matrix: the backward pass adds the
     // children's composites to it (no zero-initialisation pass, and the backward pass never reads R, o, v, a again).
+    // Along a chain segment (parent(i) == i - 1) the parent's pose and motion are carried in registers; rec[i] receives them
+    // only when a link other than i + 1 hangs off link i (m.keep(i)).
     static MPCF_HD void forward(const MP &m, const double *q, const double *qd, const double *qdd, TreeRec *rec, TreeComp *comp)
     {
         const int n = m.n();
+        double Rc[9], oc[3], vc[6], ac[6];  // link i - 1, then link i
         for (int i = 0; i < n; ++i) {
             const int par = m.parent(i);
             TreeRec &r = rec[i];
@@ -55,25 +58,30 @@ struct TreeDerivs {
                 Rl[3 * k + 1] = m.Rp(i, 3 * k + 1) * c - m.Rp(i, 3 * k) * s;
                 Rl[3 * k + 2] = m.Rp(i, 3 * k + 2);
             }
-            double vp[6], ap[6];
+            double Rn[9], on[3], vp[6], ap[6];
             if (par < 0) {
-                for (int k = 0; k < 9; ++k) r.R[k] = Rl[k];
-                for (int k = 0; k < 3; ++k) r.o[k] = m.pp(i, k);
+                for (int k = 0; k < 9; ++k) Rn[k] = Rl[k];
+                for (int k = 0; k < 3; ++k) on[k] = m.pp(i, k);
                 for (int k = 0; k < 6; ++k) { vp[k] = 0.0; ap[k] = 0.0; }
                 ap[0] = -m.grav(0); ap[1] = -m.grav(1); ap[2] = -m.grav(2);
             } else {
-                const TreeRec &p = rec[par];
-                for (int a = 0; a < 3; ++a) {
-                    for (int b = 0; b < 3; ++b) r.R[3 * a + b] = p.R[3 * a] * Rl[b] + p.R[3 * a + 1] * Rl[3 + b] + p.R[3 * a + 2] * Rl[6 + b];
-                    r.o[a] = p.o[a] + p.R[3 * a] * m.pp(i, 0) + p.R[3 * a + 1] * m.pp(i, 1) + p.R[3 * a + 2] * m.pp(i, 2);
+                if (par != i - 1) {
+                    const TreeRec &p = rec[par];
+                    for (int k = 0; k < 9; ++k) Rc[k] = p.R[k];
+                    for (int k = 0; k < 3; ++k) oc[k] = p.o[k];
+                    for (int k = 0; k < 6; ++k) { vc[k] = p.v[k]; ac[k] = p.a[k]; }
                 }
-                for (int k = 0; k < 6; ++k) { vp[k] = p.v[k]; ap[k] = p.a[k]; }
+                for (int a = 0; a < 3; ++a) {
+                    for (int b = 0; b < 3; ++b) Rn[3 * a + b] = Rc[3 * a] * Rl[b] + Rc[3 * a + 1] * Rl[3 + b] + Rc[3 * a + 2] * Rl[6 + b];
+                    on[a] = oc[a] + Rc[3 * a] * m.pp(i, 0) + Rc[3 * a + 1] * m.pp(i, 1) + Rc[3 * a + 2] * m.pp(i, 2);
+                }
+                for (int k = 0; k < 6; ++k) { vp[k] = vc[k]; ap[k] = ac[k]; }
             }
-            const double z[3] = {r.R[2], r.R[5], r.R[8]};
+            const double z[3] = {Rn[2], Rn[5], Rn[8]};
             if (pris) {  // the joint shifts the link along its axis; the axis is a pure translation
-                for (int k = 0; k < 3; ++k) { r.o[k] += z[k] * q[i]; r.K.S[k] = z[k]; r.K.S[3 + k] = 0.0; }
+                for (int k = 0; k < 3; ++k) { on[k] += z[k] * q[i]; r.K.S[k] = z[k]; r.K.S[3 + k] = 0.0; }
             } else {
-                cross3(r.o, z, r.K.S);
+                cross3(on, z, r.K.S);
                 r.K.S[3] = z[0]; r.K.S[4] = z[1]; r.K.S[5] = z[2];
             }
             // xi = S x v_parent ; eta = S x a_parent - xi x v_parent
@@ -82,12 +90,19 @@ struct TreeDerivs {
             mxm(r.K.S, ap, r.K.eta);
             mxm(r.K.xi, vp, t6);
             for (int k = 0; k < 6; ++k) r.K.eta[k] -= t6[k];
+            for (int k = 0; k < 9; ++k) Rc[k] = Rn[k];
+            for (int k = 0; k < 3; ++k) oc[k] = on[k];
             for (int k = 0; k < 6; ++k) {
-                r.v[k] = vp[k] + r.K.S[k] * qd[i];
-                r.a[k] = ap[k] + r.K.S[k] * qdd[i] - r.K.xi[k] * qd[i];
+                vc[k] = vp[k] + r.K.S[k] * qd[i];
+                ac[k] = ap[k] + r.K.S[k] * qdd[i] - r.K.xi[k] * qd[i];
+            }
+            if (m.keep(i)) {
+                for (int k = 0; k < 9; ++k) r.R[k] = Rc[k];
+                for (int k = 0; k < 3; ++k) r.o[k] = oc[k];
+                for (int k = 0; k < 6; ++k) { r.v[k] = vc[k]; r.a[k] = ac[k]; }
             }
             TreeComp &own = comp[i];
-            FdDerivs<MP, 1>::link_world(m, i, r.R, r.o, r.v, r.a, own.I, own.H, own.F, own.B);
+            FdDerivs<MP, 1>::link_world(m, i, Rc, oc, vc, ac, own.I, own.H, own.F, own.B);
         }
     }
 
@@ -98,9 +113,20 @@ struct TreeDerivs {
     static MPCF_HD void backward(const MP &m, const TreeRec *rec, TreeComp *comp, double *Mp, Out &out)
     {
         const int n = m.n();
+        TreeComp c;         // composite of the subtree of the link in hand; carried in registers to the parent along chain segments
+        bool carried = false;
         for (int k = n - 1; k >= 0; --k) {
             const TreeRec &r = rec[k];
-            TreeComp &c = comp[k];  // own values (forward pass) + the composites of the children already visited
+            {
+                const TreeComp &own = comp[k];  // own values (forward pass) + the composites of the children that stored theirs
+                if (carried) {
+                    c.I.m += own.I.m;
+                    for (int e = 0; e < 3; ++e) c.I.h[e] += own.I.h[e];
+                    for (int e = 0; e < 6; ++e) { c.I.Io[e] += own.I.Io[e]; c.H[e] += own.H[e]; c.F[e] += own.F[e]; c.B[e] += own.B[e]; }
+                } else {
+                    c = own;
+                }
+            }
             double rk[6], sk[3], gk[6], gvk[6];
             FdDerivs<MP, 1>::pair_vectors(c.I, c.H, c.F, c.B, r.K, rk, sk, gk, gvk);
             const int row = m.rowptr(k);
@@ -113,7 +139,8 @@ struct TreeDerivs {
                 out.pair(k, j, e, dqkj, dvkj, j != k ? dot6(Kj.S, gk) : dqkj, j != k ? dot6(Kj.S, gvk) : dvkj);
             }
             const int par = m.parent(k);
-            if (par >= 0) {
+            carried = par >= 0 && par == k - 1;
+            if (par >= 0 && !carried) {
                 TreeComp &p = comp[par];
                 p.I.m += c.I.m;
                 for (int e = 0; e < 3; ++e) p.I.h[e] += c.I.h[e];

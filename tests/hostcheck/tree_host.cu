@@ -16,6 +16,12 @@ struct HostTree {
     static constexpr bool kStatic = false;
     int n_;
     const int *par, *jt, *dep, *rp;
+    MPCF_HD bool keep(int i) const  // a link other than i + 1 hangs off link i
+    {
+        for (int c = i + 2; c < n_; ++c)
+            if (par[c] == i) return true;
+        return false;
+    }
     const double *Rp_, *pp_, *mass_, *mc_, *Io_, *arm_, *grav_;
     MPCF_HD int n() const { return n_; }
     MPCF_HD int parent(int i) const { return par[i]; }
