@@ -38,7 +38,7 @@
 #define MPCF_T1_BLOCKS 2
 #endif
 #ifndef MPCF_T2_BLOCKS
-#define MPCF_T2_BLOCKS 3
+#define MPCF_T2_BLOCKS 2
 #endif
 
 namespace mpcf {
@@ -937,9 +937,9 @@ static cudaError_t run_tree(const LaunchModel &m, int npat, long U, long cnt, co
     long Uc = (long)((ws_bytes - scratch_bytes) / per_unit);
     Uc -= Uc % 32;
     if (Uc < 32) return cudaErrorInvalidValue;
-    // whole waves of the derivative kernel (thread = (unit, stage), three 128-thread blocks per SM: 96 units per SM and wave):
-    // a chunk of 2.34 waves leaves its last wave a third full (measured: 28,416-unit chunks +2.5 % over 32,768 on 148 SMs)
-    const long wave = (long)nsm * 96;
+    // whole waves of the derivative kernel (thread = (unit, stage), MPCF_T2_BLOCKS 128-thread blocks per SM): a chunk that ends
+    // in a partly filled wave wastes it (measured: 28,416-unit chunks +2.5 % over 32,768 on 148 SMs)
+    const long wave = (long)nsm * MPCF_T2_BLOCKS * 32;
     if (Uc > wave) Uc -= Uc % wave;
     double *scratch = ws + (size_t)Uc * tree_ws_doubles_per_unit(n, npat);
     const size_t smem12 = blob_smem_bytes(n);
@@ -983,7 +983,7 @@ size_t tree_jvp_workspace_bytes(int n, int npat, long U)
     units = (units + 31) / 32 * 32;
     int dev = 0, nsm = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    const long wave = (long)nsm * 96;  // ... cut to whole waves of the derivative kernel (see run_tree)
+    const long wave = (long)nsm * MPCF_T2_BLOCKS * 32;  // ... cut to whole waves of the derivative kernel (see run_tree)
     if (units > wave) units -= units % wave;
     const size_t scratch = (size_t)148 * 4 * 2 * 40 * 128 * sizeof(double);  // generous: up to 2x the CTAs of a 148-SM part
     return (size_t)units * tree_ws_doubles_per_unit(n, npat) * sizeof(double) + scratch;

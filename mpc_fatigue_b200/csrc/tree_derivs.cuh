@@ -114,30 +114,21 @@ struct TreeDerivs {
     {
         const int n = m.n();
         TreeComp c;         // composite of the subtree of the link in hand; carried in registers to the parent along chain segments
+        c.I.m = 0.0;        // (never read before take() assigns it; this only tells the compiler so)
+        for (int e = 0; e < 3; ++e) c.I.h[e] = 0.0;
+        for (int e = 0; e < 6; ++e) { c.I.Io[e] = 0.0; c.H[e] = 0.0; c.F[e] = 0.0; c.B[e] = 0.0; }
         bool carried = false;
-        for (int k = n - 1; k >= 0; --k) {
-            const TreeRec &r = rec[k];
-            {
-                const TreeComp &own = comp[k];  // own values (forward pass) + the composites of the children that stored theirs
-                if (carried) {
-                    c.I.m += own.I.m;
-                    for (int e = 0; e < 3; ++e) c.I.h[e] += own.I.h[e];
-                    for (int e = 0; e < 6; ++e) { c.I.Io[e] += own.I.Io[e]; c.H[e] += own.H[e]; c.F[e] += own.F[e]; c.B[e] += own.B[e]; }
-                } else {
-                    c = own;
-                }
+        auto take = [&](int k) {  // c <- comp[k] (own values + the composites of the children that stored theirs) (+ the carried one)
+            const TreeComp &own = comp[k];
+            if (carried) {
+                c.I.m += own.I.m;
+                for (int e = 0; e < 3; ++e) c.I.h[e] += own.I.h[e];
+                for (int e = 0; e < 6; ++e) { c.I.Io[e] += own.I.Io[e]; c.H[e] += own.H[e]; c.F[e] += own.F[e]; c.B[e] += own.B[e]; }
+            } else {
+                c = own;
             }
-            double rk[6], sk[3], gk[6], gvk[6];
-            FdDerivs<MP, 1>::pair_vectors(c.I, c.H, c.F, c.B, r.K, rk, sk, gk, gvk);
-            const int row = m.rowptr(k);
-            for (int j = k; j >= 0; j = m.parent(j)) {
-                const LinkFwd &Kj = rec[j].K;
-                const double dqkj = -(dot6(rk, Kj.eta) + dot3(sk, Kj.xi + 3));
-                const double dvkj = dot3(sk, Kj.S + 3) - 2.0 * dot6(rk, Kj.xi);
-                const int e = row + m.depth(j);
-                Mp[e] = dot6(rk, Kj.S) + (j == k ? m.arm(k) : 0.0);
-                out.pair(k, j, e, dqkj, dvkj, j != k ? dot6(Kj.S, gk) : dqkj, j != k ? dot6(Kj.S, gvk) : dvkj);
-            }
+        };
+        auto hand_up = [&](int k) {  // after link k: its composite goes to the parent, in registers when the parent comes next
             const int par = m.parent(k);
             carried = par >= 0 && par == k - 1;
             if (par >= 0 && !carried) {
@@ -146,6 +137,39 @@ struct TreeDerivs {
                 for (int e = 0; e < 3; ++e) p.I.h[e] += c.I.h[e];
                 for (int e = 0; e < 6; ++e) { p.I.Io[e] += c.I.Io[e]; p.H[e] += c.H[e]; p.F[e] += c.F[e]; p.B[e] += c.B[e]; }
             }
+        };
+        auto emit = [&](int k, int j, int row, const LinkFwd &Kj, const double *rk, const double *sk, const double *gk, const double *gvk) {
+            const double dqkj = -(dot6(rk, Kj.eta) + dot3(sk, Kj.xi + 3));
+            const double dvkj = dot3(sk, Kj.S + 3) - 2.0 * dot6(rk, Kj.xi);
+            const int e = row + m.depth(j);
+            Mp[e] = dot6(rk, Kj.S) + (j == k ? m.arm(k) : 0.0);
+            out.pair(k, j, e, dqkj, dvkj, j != k ? dot6(Kj.S, gk) : dqkj, j != k ? dot6(Kj.S, gvk) : dvkj);
+        };
+        for (int k = n - 1; k >= 0;) {
+            take(k);
+            double rk[6], sk[3], gk[6], gvk[6];
+            FdDerivs<MP, 1>::pair_vectors(c.I, c.H, c.F, c.B, rec[k].K, rk, sk, gk, gvk);
+            const int row = m.rowptr(k), p = m.parent(k);
+            if (p != k - 1 || p < 0) {  // a link whose parent is elsewhere (or a root): its ancestors on their own
+                for (int j = k; j >= 0; j = m.parent(j)) emit(k, j, row, rec[j].K, rk, sk, gk, gvk);
+                hand_up(k);
+                k -= 1;
+                continue;
+            }
+            // link k and its parent p = k - 1 share every ancestor from p upwards: one pass, each (S, xi, eta) record read once
+            emit(k, k, row, rec[k].K, rk, sk, gk, gvk);
+            hand_up(k);  // carried
+            take(p);
+            double rp[6], sp[3], gp[6], gvp[6];
+            FdDerivs<MP, 1>::pair_vectors(c.I, c.H, c.F, c.B, rec[p].K, rp, sp, gp, gvp);
+            const int rowp = m.rowptr(p);
+            for (int j = p; j >= 0; j = m.parent(j)) {
+                const LinkFwd Kj = rec[j].K;
+                emit(k, j, row, Kj, rk, sk, gk, gvk);
+                emit(p, j, rowp, Kj, rp, sp, gp, gvp);
+            }
+            hand_up(p);
+            k -= 2;
         }
     }
 
