@@ -1,3 +1,6 @@
+"""Throughput of the tree Jacobian pipeline (37-joint tree, 113,664 units) against the chunk size the caller's workspace allows:
+the entry cuts its chunks to whole waves of the derivative kernel (kernels_tree.cu: run_tree), this script shows why.
+    python profiles/chunk_test.py        (GPU)"""
 import ctypes as C, sys, time
 sys.path.insert(0, '/root/repo')
 import torch
